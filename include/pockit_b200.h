@@ -1,0 +1,155 @@
+/*
+ * pockit_b200.h -- C ABI of the B200 evaluation engine for pockit's NLP callbacks.
+ *
+ * This is the drop-in boundary for the hot path: every pk_eval_* entry point
+ * replaces one SystemBase callback of the reference (file:line cited per
+ * function, all in /root/reference/pockit/base/systembase.py).  Plain pointers
+ * and sizes only; host buffers are caller-owned (NumPy arrays on the Python
+ * side, pinned when obtained from pk_alloc_host).  All functions return 0 on
+ * success; on failure pk_last_error() describes what happened.  An engine
+ * owns one CUDA stream and is not thread-safe; independent engines may run
+ * concurrently (batched sweeps, one process per GPU).
+ *
+ * The engine is *data driven*: the host planner (pockit_b200/plan.py) lowers a
+ * model to
+ *   - CUDA C for the per-node programs (JIT-compiled here with NVRTC for sm_100a),
+ *   - a table of jobs for the hand-written expansion / reduction kernels,
+ *   - constant pools (integration blocks, mesh fractions, weights).
+ */
+#ifndef POCKIT_B200_H
+#define POCKIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_ABI_VERSION 1
+
+typedef struct pk_engine pk_engine;
+
+/* evaluation modes = the reference callbacks */
+enum {
+  PK_MODE_OBJECTIVE = 0,   /* SystemBase.objective   systembase.py:602 */
+  PK_MODE_CONSTRAINTS = 1, /* SystemBase.constraints systembase.py:613 */
+  PK_MODE_GRADIENT = 2,    /* SystemBase.gradient    systembase.py:646 */
+  PK_MODE_JACOBIAN = 3,    /* SystemBase.jacobian    systembase.py:676 */
+  PK_MODE_HESSIAN = 4,     /* SystemBase.hessian     systembase.py:820 (hessian_o :735, hessian_c :786) */
+  PK_N_MODES = 5
+};
+
+/* job stages (which hand-written kernel consumes the record) */
+enum {
+  PK_STAGE_REDUCE = 0,      /* row sums of the node table -> scalar table (quadrature, np.add.at on broadcast columns) */
+  PK_STAGE_DEFECT = 1,      /* T.x - dt * (I.f)           phasebase.py:1008-1012 */
+  PK_STAGE_GENERIC = 2,     /* const / kron / table-expand / scaled / sys / outer / tril slot runs */
+  PK_STAGE_EXPAND = 3,      /* block-structured expansion through the integration operator, phasebase.py:1120-1124, 1280-1285 */
+  PK_STAGE_GRAD_RANGE = 4,  /* gather-sum into per-node gradient columns, systembase.py:654-656 */
+  PK_STAGE_GRAD_SCALAR = 5, /* gather-sum into scalar gradient columns */
+  PK_N_STAGES = 6
+};
+
+/* generic job types (PK_STAGE_GENERIC) */
+enum {
+  PK_JOB_CONST = 0,
+  PK_JOB_KRON = 1,
+  PK_JOB_EXPAND_TABLE = 2,
+  PK_JOB_SCALED = 3,
+  PK_JOB_SYS = 4,
+  PK_JOB_OUTER = 5,
+  PK_JOB_TRIL = 6
+};
+
+/* One record for every stage; the meaning of i[] / f[] per stage and type is
+ * documented next to the kernels in pockit_b200/csrc/pk_kernels.cuh. */
+typedef struct {
+  int32_t type;
+  int32_t flags;
+  int64_t i[16];
+  double f[2];
+} pk_job;
+
+/* problem dimensions, fixed for the life of an engine */
+typedef struct {
+  int32_t abi_version; /* PK_ABI_VERSION */
+  int32_t batch;       /* B: independent instances evaluated per call (>= 1) */
+  int64_t L;           /* variables per instance                     (SystemBase.L) */
+  int64_t m;           /* constraints per instance                   (len(c_lb)) */
+  int64_t nnz_jac;     /* len(jacobianstructure()[0]) */
+  int64_t nnz_hess;    /* len(hessianstructure()[0]), objective part first */
+  int64_t n_scalar;    /* scalar-table slots per instance */
+  int64_t n_table;     /* node-table doubles in total (all rows, all instances) */
+  int64_t n_fixed;     /* FIXED boundary values per instance */
+} pk_dims;
+
+/* one per-node program (one phase) of a mode */
+typedef struct {
+  const char *kernel;  /* NVRTC kernel name */
+  int64_t n_nodes;     /* collocation nodes L_m of the phase */
+  int64_t tm_offset;   /* offsets into the double pool: mesh fractions, quadrature weights */
+  int64_t wm_offset;
+} pk_node_program;
+
+typedef struct {
+  const char *cuda_source;           /* all node programs + the system program of this mode */
+  const char *const *nvrtc_options;  /* extra options (the engine adds -arch and the std ones) */
+  int32_t n_nvrtc_options;
+  int32_t n_node_programs;
+  const pk_node_program *node_programs;
+  const char *system_kernel;         /* NULL: no system-level function in this mode */
+  const char *table_symbol;          /* __constant__ long long[] the programs index */
+  const int64_t *table;
+  int64_t n_table_entries;
+  int64_t n_scalar;                  /* scalar-table stride of this mode (<= pk_dims.n_scalar) */
+  int64_t n_out;                     /* outputs per instance */
+  const pk_job *jobs[PK_N_STAGES];
+  int64_t n_jobs[PK_N_STAGES];
+} pk_mode_desc;
+
+int pk_abi_version(void);
+const char *pk_last_error(void);
+int pk_device_count(int *count);
+
+int pk_engine_create(const pk_dims *dims, int device, pk_engine **out);
+int pk_engine_destroy(pk_engine *e);
+
+/* constant pools shared by all modes (uploaded once per discretisation) */
+int pk_engine_set_pools(pk_engine *e, const double *dpool, int64_t n_double, const int64_t *ipool, int64_t n_int);
+/* FIXED boundary values, instance-major [batch][n_fixed] */
+int pk_engine_set_fixed(pk_engine *e, const double *values);
+/* compile (NVRTC, sm_100a) and install one mode; returns the build log through pk_last_error on failure */
+int pk_engine_load_mode(pk_engine *e, int mode, const pk_mode_desc *desc);
+/* cubin of a loaded mode (for caching / inspection); *size = 0 if not loaded */
+int pk_engine_get_cubin(pk_engine *e, int mode, const void **data, size_t *size);
+
+/* ---- host-to-host callbacks: x (and multipliers) in, values out; instance-major for batch > 1 ---- */
+int pk_eval_objective(pk_engine *e, const double *x, double *f /* [B] */);
+int pk_eval_gradient(pk_engine *e, const double *x, double *grad /* [B][L] */);
+int pk_eval_constraints(pk_engine *e, const double *x, double *c /* [B][m] */);
+int pk_eval_jacobian(pk_engine *e, const double *x, double *values /* [B][nnz_jac] */);
+int pk_eval_hessian(pk_engine *e, const double *x, const double *lambda /* [B][m] */,
+                    const double *sigma /* [B] */, double *values /* [B][nnz_hess] */);
+
+/* ---- device-resident path (inputs already in HBM): upload once, run many, download ---- */
+int pk_upload_x(pk_engine *e, const double *x);
+int pk_upload_multipliers(pk_engine *e, const double *lambda, const double *sigma);
+int pk_run(pk_engine *e, int mode);               /* enqueue the mode's kernels on the engine stream */
+int pk_sync(pk_engine *e);
+int pk_download(pk_engine *e, int mode, double *out);
+/* time `iters` back-to-back runs with CUDA events on the engine stream; ms_total covers the
+ * whole mode, ms_stage[s] the kernels of each stage (s = 0..PK_N_STAGES-1 jobs, PK_N_STAGES = node
+ * programs, PK_N_STAGES+1 = system program), measured in separate passes. */
+int pk_time(pk_engine *e, int mode, int iters, float *ms_total, float *ms_stage /* [PK_N_STAGES+2] */);
+int pk_kernel_launches(pk_engine *e, int64_t *count); /* kernels launched so far by this engine */
+int pk_flush_l2(pk_engine *e);                        /* overwrite a buffer larger than L2 */
+
+/* pinned host memory for zero-copy NumPy views */
+void *pk_alloc_host(size_t bytes);
+void pk_free_host(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POCKIT_B200_H */

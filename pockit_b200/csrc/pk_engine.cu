@@ -1,0 +1,457 @@
+// pk_engine.cu -- host side of the C ABI (include/pockit_b200.h): device memory, one stream,
+// NVRTC compilation of the generated per-node programs for sm_100a, and the launch sequences
+// of the five callbacks.
+//
+// Launch sequence of a mode (all on the engine stream):
+//   node programs (one per phase, NVRTC)  ->  pk_reduce_rows  ->  system program (NVRTC)
+//   ->  pk_defects | pk_generic_jobs + pk_expand_blocks | pk_grad_range + pk_grad_scalar
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pk_kernels.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +         \
+                  std::to_string(__LINE__) + ")");                                                 \
+  } while (0)
+
+struct ModeState {
+  bool loaded = false;
+  cudaLibrary_t lib = nullptr;
+  std::vector<cudaKernel_t> node_kernels;
+  std::vector<pk_node_program> node_programs;
+  cudaKernel_t sys_kernel = nullptr;
+  long long n_scalar = 0, n_out = 0;
+  std::vector<char> cubin;
+  pk_job* jobs[PK_N_STAGES] = {};
+  long long n_jobs[PK_N_STAGES] = {};
+  // block -> (job, chunk) maps of the two slot-streaming kernels
+  int* gen_job = nullptr; int* gen_chunk = nullptr; long long gen_blocks = 0;
+  int* exp_job = nullptr; int* exp_chunk = nullptr; long long exp_blocks = 0;
+  size_t exp_smem = 0;
+  long long max_defect_rows = 0, max_grad_count = 0;
+};
+
+struct pk_engine {
+  pk_dims dims;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double *X = nullptr, *LAM = nullptr, *SIG = nullptr, *S = nullptr, *W = nullptr, *OUT = nullptr, *FIX = nullptr;
+  double* dpool = nullptr; long long* ipool = nullptr;
+  double *hX = nullptr, *hLAM = nullptr, *hSIG = nullptr, *hOUT = nullptr;  // pinned staging
+  double* flush = nullptr; long long n_flush = 0;
+  long long n_out_max = 0;
+  ModeState mode[PK_N_MODES];
+  long long launches = 0;
+};
+
+extern "C" int pk_abi_version(void) { return PK_ABI_VERSION; }
+extern "C" const char* pk_last_error(void) { return g_err.c_str(); }
+
+extern "C" int pk_device_count(int* count) {
+  CK(cudaGetDeviceCount(count));
+  return 0;
+}
+
+extern "C" void* pk_alloc_host(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void pk_free_host(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
+  if (!d || !out) return fail("pk_engine_create: null argument");
+  if (d->abi_version != PK_ABI_VERSION) return fail("pk_engine_create: ABI version mismatch");
+  if (d->batch < 1) return fail("pk_engine_create: batch must be >= 1");
+  int n = 0;
+  CK(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) return fail("pk_engine_create: no such CUDA device");
+  CK(cudaSetDevice(device));
+  pk_engine* e = new pk_engine();
+  e->dims = *d;
+  e->device = device;
+  const long long B = d->batch;
+  long long n_out = d->L;
+  if (d->m > n_out) n_out = d->m;
+  if (d->nnz_jac > n_out) n_out = d->nnz_jac;
+  if (d->nnz_hess > n_out) n_out = d->nnz_hess;
+  if (n_out < 1) n_out = 1;
+  e->n_out_max = n_out;
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  auto dev = [&](double** p, long long count) { return cudaMalloc((void**)p, sizeof(double) * (size_t)(count > 0 ? count : 1)); };
+  CK(dev(&e->X, B * d->L));
+  CK(dev(&e->LAM, B * d->m));
+  CK(dev(&e->SIG, B));
+  CK(dev(&e->S, B * d->n_scalar));
+  CK(dev(&e->W, d->n_table));
+  CK(dev(&e->OUT, B * n_out));
+  CK(dev(&e->FIX, B * d->n_fixed));
+  CK(cudaMemsetAsync(e->LAM, 0, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1), e->stream));
+  CK(cudaMemsetAsync(e->SIG, 0, sizeof(double) * (size_t)B, e->stream));
+  CK(cudaMemsetAsync(e->S, 0, sizeof(double) * (size_t)(B * d->n_scalar > 0 ? B * d->n_scalar : 1), e->stream));
+  CK(cudaMallocHost((void**)&e->hX, sizeof(double) * (size_t)(B * d->L > 0 ? B * d->L : 1)));
+  CK(cudaMallocHost((void**)&e->hLAM, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1)));
+  CK(cudaMallocHost((void**)&e->hSIG, sizeof(double) * (size_t)B));
+  CK(cudaMallocHost((void**)&e->hOUT, sizeof(double) * (size_t)(B * n_out)));
+  CK(cudaStreamSynchronize(e->stream));
+  *out = e;
+  return 0;
+}
+
+static void free_mode(ModeState& ms) {
+  for (int s = 0; s < PK_N_STAGES; ++s) {
+    if (ms.jobs[s]) cudaFree(ms.jobs[s]);
+    ms.jobs[s] = nullptr;
+  }
+  if (ms.gen_job) cudaFree(ms.gen_job);
+  if (ms.gen_chunk) cudaFree(ms.gen_chunk);
+  if (ms.exp_job) cudaFree(ms.exp_job);
+  if (ms.exp_chunk) cudaFree(ms.exp_chunk);
+  if (ms.lib) cudaLibraryUnload(ms.lib);
+  ms = ModeState();
+}
+
+extern "C" int pk_engine_destroy(pk_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto& ms : e->mode) free_mode(ms);
+  cudaFree(e->X); cudaFree(e->LAM); cudaFree(e->SIG); cudaFree(e->S); cudaFree(e->W); cudaFree(e->OUT);
+  cudaFree(e->FIX); cudaFree(e->dpool); cudaFree(e->ipool); cudaFree(e->flush);
+  cudaFreeHost(e->hX); cudaFreeHost(e->hLAM); cudaFreeHost(e->hSIG); cudaFreeHost(e->hOUT);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return 0;
+}
+
+extern "C" int pk_engine_set_pools(pk_engine* e, const double* dp, int64_t nd, const int64_t* ip, int64_t ni) {
+  if (!e) return fail("pk_engine_set_pools: null engine");
+  CK(cudaSetDevice(e->device));
+  cudaFree(e->dpool); cudaFree(e->ipool);
+  e->dpool = nullptr; e->ipool = nullptr;
+  CK(cudaMalloc((void**)&e->dpool, sizeof(double) * (size_t)(nd > 0 ? nd : 1)));
+  CK(cudaMalloc((void**)&e->ipool, sizeof(long long) * (size_t)(ni > 0 ? ni : 1)));
+  if (nd > 0) CK(cudaMemcpy(e->dpool, dp, sizeof(double) * (size_t)nd, cudaMemcpyHostToDevice));
+  if (ni > 0) CK(cudaMemcpy(e->ipool, ip, sizeof(long long) * (size_t)ni, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int pk_engine_set_fixed(pk_engine* e, const double* v) {
+  if (!e) return fail("pk_engine_set_fixed: null engine");
+  CK(cudaSetDevice(e->device));
+  const size_t n = (size_t)e->dims.batch * (size_t)e->dims.n_fixed;
+  if (n) CK(cudaMemcpy(e->FIX, v, sizeof(double) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int compile(const pk_mode_desc* d, int device, std::vector<char>& cubin) {
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, d->cuda_source, "pockit_b200_generated.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    return fail("nvrtcCreateProgram failed");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  // B200 is sm_100: compile for the arch-specific target; anything else gets its own real arch
+  std::string arch = "--gpu-architecture=sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                     ((prop.major == 10 && prop.minor == 0) ? "a" : "");
+  std::vector<const char*> opts = {arch.c_str(), "--std=c++17", "-lineinfo", "--fmad=false"};
+  for (int i = 0; i < d->n_nvrtc_options; ++i) opts.push_back(d->nvrtc_options[i]);
+  nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    return fail("NVRTC compilation failed:\n" + log);
+  }
+  size_t n = 0;
+  if (nvrtcGetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) {
+    nvrtcDestroyProgram(&prog);
+    return fail("NVRTC produced no cubin");
+  }
+  cubin.resize(n);
+  nvrtcGetCUBIN(prog, cubin.data());
+  nvrtcDestroyProgram(&prog);
+  return 0;
+}
+
+static int build_block_map(const pk_job* jobs, long long n, int** d_job, int** d_chunk, long long* n_blocks) {
+  std::vector<int> bj, bc;
+  for (long long j = 0; j < n; ++j) {
+    const long long chunks = (jobs[j].i[1] + PK_CHUNK - 1) / PK_CHUNK;
+    for (long long c = 0; c < chunks; ++c) {
+      bj.push_back((int)j);
+      bc.push_back((int)c);
+    }
+  }
+  *n_blocks = (long long)bj.size();
+  if (bj.empty()) return 0;
+  CK(cudaMalloc((void**)d_job, sizeof(int) * bj.size()));
+  CK(cudaMalloc((void**)d_chunk, sizeof(int) * bc.size()));
+  CK(cudaMemcpy(*d_job, bj.data(), sizeof(int) * bj.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(*d_chunk, bc.data(), sizeof(int) * bc.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d) {
+  if (!e || !d) return fail("pk_engine_load_mode: null argument");
+  if (mode < 0 || mode >= PK_N_MODES) return fail("pk_engine_load_mode: bad mode");
+  CK(cudaSetDevice(e->device));
+  ModeState& ms = e->mode[mode];
+  free_mode(ms);
+  if (d->n_scalar > e->dims.n_scalar) return fail("pk_engine_load_mode: n_scalar exceeds pk_dims.n_scalar");
+  if (d->n_out > e->n_out_max) return fail("pk_engine_load_mode: n_out exceeds the engine's output buffer");
+  if (compile(d, e->device, ms.cubin)) return 1;
+  CK(cudaLibraryLoadData(&ms.lib, ms.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  for (int i = 0; i < d->n_node_programs; ++i) {
+    cudaKernel_t k;
+    CK(cudaLibraryGetKernel(&k, ms.lib, d->node_programs[i].kernel));
+    ms.node_kernels.push_back(k);
+    ms.node_programs.push_back(d->node_programs[i]);
+    ms.node_programs.back().kernel = nullptr;
+  }
+  if (d->system_kernel) CK(cudaLibraryGetKernel(&ms.sys_kernel, ms.lib, d->system_kernel));
+  if (d->n_table_entries > 0) {
+    void* dptr = nullptr;
+    size_t bytes = 0;
+    CK(cudaLibraryGetGlobal(&dptr, &bytes, ms.lib, d->table_symbol));
+    if (bytes < sizeof(long long) * (size_t)d->n_table_entries) return fail("constant table smaller than its contents");
+    CK(cudaMemcpy(dptr, d->table, sizeof(long long) * (size_t)d->n_table_entries, cudaMemcpyHostToDevice));
+  }
+  ms.n_scalar = d->n_scalar;
+  ms.n_out = d->n_out;
+  for (int s = 0; s < PK_N_STAGES; ++s) {
+    ms.n_jobs[s] = d->n_jobs[s];
+    if (d->n_jobs[s] > 0) {
+      CK(cudaMalloc((void**)&ms.jobs[s], sizeof(pk_job) * (size_t)d->n_jobs[s]));
+      CK(cudaMemcpy(ms.jobs[s], d->jobs[s], sizeof(pk_job) * (size_t)d->n_jobs[s], cudaMemcpyHostToDevice));
+    }
+  }
+  if (build_block_map(d->jobs[PK_STAGE_GENERIC], d->n_jobs[PK_STAGE_GENERIC], &ms.gen_job, &ms.gen_chunk, &ms.gen_blocks)) return 1;
+  if (build_block_map(d->jobs[PK_STAGE_EXPAND], d->n_jobs[PK_STAGE_EXPAND], &ms.exp_job, &ms.exp_chunk, &ms.exp_blocks)) return 1;
+  for (long long j = 0; j < d->n_jobs[PK_STAGE_EXPAND]; ++j) {
+    const pk_job& jb = d->jobs[PK_STAGE_EXPAND][j];
+    const size_t sm = sizeof(double) * (size_t)(jb.i[3] * jb.i[4]);
+    if (sm > ms.exp_smem) ms.exp_smem = sm;
+    if (jb.i[1] >= (1LL << 32)) return fail("expand job longer than 2^32 slots");
+  }
+  if (ms.exp_smem > 48 * 1024) {
+    if (ms.exp_smem > 200 * 1024) return fail("integration block too large for shared memory");
+    CK(cudaFuncSetAttribute(pk_expand_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.exp_smem));
+  }
+  for (long long j = 0; j < d->n_jobs[PK_STAGE_DEFECT]; ++j) {
+    const long long r = d->jobs[PK_STAGE_DEFECT][j].i[4] * d->jobs[PK_STAGE_DEFECT][j].i[3];
+    if (r > ms.max_defect_rows) ms.max_defect_rows = r;
+  }
+  for (long long j = 0; j < d->n_jobs[PK_STAGE_GRAD_RANGE]; ++j)
+    if (d->jobs[PK_STAGE_GRAD_RANGE][j].i[1] > ms.max_grad_count) ms.max_grad_count = d->jobs[PK_STAGE_GRAD_RANGE][j].i[1];
+  ms.loaded = true;
+  return 0;
+}
+
+extern "C" int pk_engine_get_cubin(pk_engine* e, int mode, const void** data, size_t* size) {
+  if (!e || mode < 0 || mode >= PK_N_MODES) return fail("pk_engine_get_cubin: bad argument");
+  *data = e->mode[mode].cubin.data();
+  *size = e->mode[mode].cubin.size();
+  return 0;
+}
+
+static PkCtx make_ctx(pk_engine* e, const ModeState& ms) {
+  PkCtx cx;
+  cx.X = e->X; cx.LAM = e->LAM; cx.SIG = e->SIG; cx.S = e->S; cx.W = e->W; cx.OUT = e->OUT;
+  cx.dpool = e->dpool; cx.ipool = e->ipool;
+  cx.L = e->dims.L; cx.m = e->dims.m; cx.n_scalar = ms.n_scalar; cx.n_out = ms.n_out;
+  return cx;
+}
+
+static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// stage_mask selects which parts run (bit s = job stage s, bit PK_N_STAGES = node programs,
+// bit PK_N_STAGES + 1 = system program); used by pk_time to attribute time.
+static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
+  ModeState& ms = e->mode[mode];
+  if (!ms.loaded) return fail("mode not loaded");
+  const int B = e->dims.batch;
+  PkCtx cx = make_ctx(e, ms);
+  cudaStream_t st = e->stream;
+  if (stage_mask & (1u << PK_N_STAGES)) {
+    for (size_t p = 0; p < ms.node_kernels.size(); ++p) {
+      const pk_node_program& np_ = ms.node_programs[p];
+      const double* tm = e->dpool + np_.tm_offset;
+      const double* wm = e->dpool + np_.wm_offset;
+      int Bi = B;
+      void* args[] = {&e->X, &e->LAM, &e->FIX, &tm, &wm, &e->S, &e->W, &e->OUT, &Bi};
+      const long long threads = (long long)B * np_.n_nodes;
+      CK(cudaLaunchKernel((void*)ms.node_kernels[p], dim3(blocks_for(threads, 128)), dim3(128), args, 0, st));
+      ++e->launches;
+    }
+  }
+  if ((stage_mask & (1u << PK_STAGE_REDUCE)) && ms.n_jobs[PK_STAGE_REDUCE]) {
+    const long long warps = ms.n_jobs[PK_STAGE_REDUCE] * (long long)B;
+    pk_reduce_rows<<<blocks_for(warps * 32, PK_THREADS), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B);
+    ++e->launches;
+  }
+  if ((stage_mask & (1u << (PK_N_STAGES + 1))) && ms.sys_kernel) {
+    int Bi = B;
+    void* args[] = {&e->X, &e->S, &e->OUT, &Bi};
+    CK(cudaLaunchKernel((void*)ms.sys_kernel, dim3(blocks_for(B, 64)), dim3(64), args, 0, st));
+    ++e->launches;
+  }
+  if ((stage_mask & (1u << PK_STAGE_DEFECT)) && ms.n_jobs[PK_STAGE_DEFECT]) {
+    dim3 grid(blocks_for(ms.max_defect_rows * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_DEFECT]);
+    pk_defects<<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+    ++e->launches;
+  }
+  if ((stage_mask & (1u << PK_STAGE_GENERIC)) && ms.gen_blocks) {
+    pk_generic_jobs<<<dim3((unsigned)ms.gen_blocks, B), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk);
+    ++e->launches;
+  }
+  if ((stage_mask & (1u << PK_STAGE_EXPAND)) && ms.exp_blocks) {
+    pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], ms.exp_job, ms.exp_chunk);
+    ++e->launches;
+  }
+  if (mode == PK_MODE_GRADIENT && (stage_mask & ((1u << PK_STAGE_GRAD_RANGE) | (1u << PK_STAGE_GRAD_SCALAR)))) {
+    CK(cudaMemsetAsync(e->OUT, 0, sizeof(double) * (size_t)B * (size_t)ms.n_out, st));
+    if (ms.n_jobs[PK_STAGE_GRAD_RANGE]) {
+      dim3 grid(blocks_for(ms.max_grad_count * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_GRAD_RANGE]);
+      pk_grad_range<<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
+      ++e->launches;
+    }
+    if (ms.n_jobs[PK_STAGE_GRAD_SCALAR]) {
+      const long long n = ms.n_jobs[PK_STAGE_GRAD_SCALAR] * (long long)B;
+      pk_grad_scalar<<<blocks_for(n, PK_THREADS), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_SCALAR], (int)ms.n_jobs[PK_STAGE_GRAD_SCALAR], B);
+      ++e->launches;
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pk_upload_x(pk_engine* e, const double* x) {
+  if (!e || !x) return fail("pk_upload_x: null argument");
+  CK(cudaSetDevice(e->device));
+  const size_t n = sizeof(double) * (size_t)e->dims.batch * (size_t)e->dims.L;
+  memcpy(e->hX, x, n);
+  CK(cudaMemcpyAsync(e->X, e->hX, n, cudaMemcpyHostToDevice, e->stream));
+  return 0;
+}
+
+extern "C" int pk_upload_multipliers(pk_engine* e, const double* lambda, const double* sigma) {
+  if (!e) return fail("pk_upload_multipliers: null engine");
+  CK(cudaSetDevice(e->device));
+  const size_t B = (size_t)e->dims.batch;
+  if (lambda && e->dims.m > 0) {
+    const size_t n = sizeof(double) * B * (size_t)e->dims.m;
+    memcpy(e->hLAM, lambda, n);
+    CK(cudaMemcpyAsync(e->LAM, e->hLAM, n, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (sigma) {
+    memcpy(e->hSIG, sigma, sizeof(double) * B);
+    CK(cudaMemcpyAsync(e->SIG, e->hSIG, sizeof(double) * B, cudaMemcpyHostToDevice, e->stream));
+  }
+  return 0;
+}
+
+extern "C" int pk_run(pk_engine* e, int mode) {
+  if (!e || mode < 0 || mode >= PK_N_MODES) return fail("pk_run: bad argument");
+  CK(cudaSetDevice(e->device));
+  return launch_mode(e, mode, ~0u);
+}
+
+extern "C" int pk_sync(pk_engine* e) {
+  if (!e) return fail("pk_sync: null engine");
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" int pk_download(pk_engine* e, int mode, double* out) {
+  if (!e || !out || mode < 0 || mode >= PK_N_MODES) return fail("pk_download: bad argument");
+  CK(cudaSetDevice(e->device));
+  const size_t n = sizeof(double) * (size_t)e->dims.batch * (size_t)e->mode[mode].n_out;
+  // `out` may be pinned (pk_alloc_host) or pageable; the runtime handles both
+  CK(cudaMemcpyAsync(out, e->OUT, n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+static int eval(pk_engine* e, int mode, const double* x, const double* lam, const double* sig, double* out) {
+  if (pk_upload_x(e, x)) return 1;
+  if (mode == PK_MODE_HESSIAN && pk_upload_multipliers(e, lam, sig)) return 1;
+  if (launch_mode(e, mode, ~0u)) return 1;
+  return pk_download(e, mode, out);
+}
+
+extern "C" int pk_eval_objective(pk_engine* e, const double* x, double* f) { return eval(e, PK_MODE_OBJECTIVE, x, nullptr, nullptr, f); }
+extern "C" int pk_eval_gradient(pk_engine* e, const double* x, double* g) { return eval(e, PK_MODE_GRADIENT, x, nullptr, nullptr, g); }
+extern "C" int pk_eval_constraints(pk_engine* e, const double* x, double* c) { return eval(e, PK_MODE_CONSTRAINTS, x, nullptr, nullptr, c); }
+extern "C" int pk_eval_jacobian(pk_engine* e, const double* x, double* v) { return eval(e, PK_MODE_JACOBIAN, x, nullptr, nullptr, v); }
+extern "C" int pk_eval_hessian(pk_engine* e, const double* x, const double* lam, const double* sig, double* v) {
+  if (!lam || !sig) return fail("pk_eval_hessian: multipliers required");
+  return eval(e, PK_MODE_HESSIAN, x, lam, sig, v);
+}
+
+extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float* ms_stage) {
+  if (!e || mode < 0 || mode >= PK_N_MODES || iters < 1) return fail("pk_time: bad argument");
+  CK(cudaSetDevice(e->device));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  auto timed = [&](unsigned mask, float* out) -> int {
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventRecord(a, e->stream));
+    for (int i = 0; i < iters; ++i)
+      if (launch_mode(e, mode, mask)) return 1;
+    CK(cudaEventRecord(b, e->stream));
+    CK(cudaEventSynchronize(b));
+    CK(cudaEventElapsedTime(out, a, b));
+    return 0;
+  };
+  if (ms_total && timed(~0u, ms_total)) return 1;
+  if (ms_stage)
+    for (int s = 0; s < PK_N_STAGES + 2; ++s) {
+      unsigned mask = 1u << s;
+      if (s == PK_STAGE_GRAD_RANGE) mask |= 1u << PK_STAGE_GRAD_SCALAR;
+      if (s == PK_STAGE_GRAD_SCALAR) { ms_stage[s] = 0.f; continue; }
+      if (timed(mask, &ms_stage[s])) return 1;
+    }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return 0;
+}
+
+extern "C" int pk_kernel_launches(pk_engine* e, int64_t* count) {
+  if (!e || !count) return fail("pk_kernel_launches: null argument");
+  *count = e->launches;
+  return 0;
+}
+
+extern "C" int pk_flush_l2(pk_engine* e) {
+  if (!e) return fail("pk_flush_l2: null engine");
+  CK(cudaSetDevice(e->device));
+  if (!e->flush) {
+    e->n_flush = (256LL << 20) / 8;  // 256 MiB > 126 MB of L2
+    CK(cudaMalloc((void**)&e->flush, sizeof(double) * (size_t)e->n_flush));
+  }
+  pk_fill<<<148 * 8, 256, 0, e->stream>>>(e->flush, e->n_flush, 1.0);
+  CK(cudaGetLastError());
+  return 0;
+}

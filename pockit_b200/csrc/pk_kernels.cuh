@@ -1,0 +1,257 @@
+// pk_kernels.cuh -- hand-written sm_100a kernels of the pockit-b200 engine.
+//
+// The per-node programs (function values / derivatives and their chain-rule
+// products) are generated per model and JIT-compiled with NVRTC; everything
+// that is *model independent* lives here and is driven by job records
+// (include/pockit_b200.h, pk_job):
+//
+//   pk_reduce_rows    quadrature sums / np.add.at on broadcast columns   (phasebase.py:1004, systembase.py:654-656)
+//   pk_defects        T.x - dt * (I.f), CSR row order                    (phasebase.py:1008-1012)
+//   pk_expand_blocks  -I[r,c] * [lam_r] * list[c] for whole interval blocks   (phasebase.py:1120-1124, 1280-1285)
+//   pk_generic_jobs   const / kron / table-expand / scaled / sys / outer / tril runs
+//   pk_grad_range / pk_grad_scalar   gather-sum of the objective gradient (systembase.py:646-657)
+//
+// All of them are HBM-bound streaming kernels: every thread produces
+// consecutive output slots (coalesced 8-byte stores, the runs are contiguous
+// in the reference's slot order by construction), sources are the small,
+// L2-resident node table W and scalar table S, and the constant pools.
+// Arithmetic association follows the reference so that results agree to the
+// last bit whenever the per-node leaves do (compiled with --fmad=false).
+//
+// Job field layout (i[] / f[] of pk_job):
+//   REDUCE   i0 W base of the row, i1 L_m, i2 c_lo, i3 c_hi, i4 scalar slot
+//   DEFECT   i0 x offset of the phase, i1 L_x, i2 L_m, i3 n_x, i4 rows per state,
+//            i5 ipool row_ptr, i6 ipool cols, i7 dpool data (full operator, row-major),
+//            i8 ipool +1 column per row, i9 ipool -1 column per row, i10 W base of f_0 (rows consecutive),
+//            i11 scalar header (dt, front values, back values), i12 first output row
+//   GENERIC  i0 dst, i1 count, i2 lam row offset (-1: none), i3 system scalar slot (-1: none),
+//            i4 post factor (0 none, 1 sigma, 2 lam[i5]), f0 sign
+//     CONST         i6 dpool values
+//     KRON          i6 dpool data[a], i7 nb, i8 first scalar slot (nb consecutive), i9 ipool lam rows[a] (F_LAM)
+//     EXPAND_TABLE  i6 ipool rows, i7 ipool cols, i8 dpool data, i9 W base, i10 L_m
+//     SCALED        i6 W base | scalar slot (F_A_SCALAR), i7 L_m, i8 c_lo
+//     SYS           -
+//     OUTER / TRIL  A: i6 i7 i8, B: i9 i10 i11 (as SCALED; F_*_SCALAR / F_*_UNIT), i12 length of B
+//   EXPAND   i0 dst, i1 count, i2 lam row of the first block row (-1), i3 n (block columns), i4 block rows,
+//            i5 node step per interval, i6 first node, i7 dpool unit block, i8 dpool widths, i9 W base, i10 L_m, f0 sign
+//   GRAD_RANGE   i0 dst, i1 count, i2 ipool contributions (W base, L_m, c_lo, system slot) x i3
+//   GRAD_SCALAR  i0 dst, i2 ipool contributions (scalar slot | -1, system slot) x i3
+#pragma once
+#include <stdint.h>
+
+#include "../../include/pockit_b200.h"
+
+#define PK_F_A_SCALAR 1
+#define PK_F_B_SCALAR 2
+#define PK_F_A_UNIT 4
+#define PK_F_B_UNIT 8
+#define PK_F_LAM 16
+
+#define PK_THREADS 256
+#define PK_ITEMS 4  // consecutive output slots per thread
+#define PK_CHUNK (PK_THREADS * PK_ITEMS)
+
+struct PkCtx {
+  const double* __restrict__ X;
+  const double* __restrict__ LAM;
+  const double* __restrict__ SIG;
+  double* __restrict__ S;
+  double* __restrict__ W;
+  double* __restrict__ OUT;
+  const double* __restrict__ dpool;
+  const long long* __restrict__ ipool;
+  long long L, m, n_scalar, n_out;
+};
+
+// ---------------------------------------------------------------------------------------------
+// one warp per (job, instance): fixed-order strided accumulation + shuffle tree (deterministic)
+__global__ void __launch_bounds__(PK_THREADS) pk_reduce_rows(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
+  const int warp = (blockIdx.x * PK_THREADS + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_jobs * B) return;
+  const int j = warp % n_jobs, b = warp / n_jobs;
+  const pk_job& jb = jobs[j];
+  const double* row = cx.W + jb.i[0] + (long long)b * jb.i[1];
+  double acc = 0.0;
+  for (long long c = jb.i[2] + lane; c < jb.i[3]; c += 32) acc += row[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) cx.S[(long long)b * cx.n_scalar + jb.i[4]] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one thread per defect row; the I.f sum runs over the row's entries in column order, dt is
+// applied after the sum, exactly like `T_v.dot(x) - I_m.dot(f) * dt`
+__global__ void __launch_bounds__(PK_THREADS) pk_defects(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
+  const pk_job& jb = jobs[blockIdx.y];
+  const long long rows = jb.i[4], n_x = jb.i[3];
+  const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
+  if (gid >= rows * n_x * B) return;
+  const int b = (int)(gid / (rows * n_x));
+  const long long rem = gid - (long long)b * rows * n_x;
+  const int i = (int)(rem / rows);
+  const long long r = rem - (long long)i * rows;
+  const long long Lx = jb.i[1], Lm = jb.i[2];
+  const double* Sb = cx.S + (long long)b * cx.n_scalar + jb.i[11];
+  const double* xv = cx.X + (long long)b * cx.L + jb.i[0] + (long long)i * Lx;
+  const double* f = cx.W + jb.i[10] + ((long long)i * B + b) * Lm;
+  const long long* ptr = cx.ipool + jb.i[5];
+  const long long* col = cx.ipool + jb.i[6];
+  const double* dat = cx.dpool + jb.i[7];
+  double acc = 0.0;
+  for (long long k = ptr[r]; k < ptr[r + 1]; ++k) acc += dat[k] * f[col[k]];
+  const long long cp = cx.ipool[jb.i[8] + r], cn = cx.ipool[jb.i[9] + r];
+  // boundary nodes read the substituted values the node program left in the scalar header
+  const double xp = cp == 0 ? Sb[1 + i] : (cp == Lx - 1 ? Sb[1 + n_x + i] : xv[cp]);
+  const double xn = cn == 0 ? Sb[1 + i] : (cn == Lx - 1 ? Sb[1 + n_x + i] : xv[cn]);
+  double tx = 0.0;
+  tx += 1.0 * xp;
+  tx += -1.0 * xn;
+  cx.OUT[(long long)b * cx.n_out + jb.i[12] + (long long)i * rows + r] = tx - acc * Sb[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-structured expansion: every interior interval contributes a dense (rows x n) block whose
+// entries are (unit[r][c] * width_K) / 2 -- the reference's `I_lgl(n) * d / 2` -- so the operator
+// never has to be read from memory: the unit block sits in shared memory and slot -> (K, r, c) is
+// pure arithmetic.  A job never exceeds 2^32 slots (the planner splits longer runs).
+__global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const pk_job* __restrict__ jobs,
+                                                              const int* __restrict__ blk_job,
+                                                              const int* __restrict__ blk_chunk) {
+  extern __shared__ double unit_s[];
+  const pk_job& jb = jobs[blk_job[blockIdx.x]];
+  const int b = blockIdx.y;
+  const int n = (int)jb.i[3], rows = (int)jb.i[4];
+  const int bn = n * rows;
+  const double* unit = cx.dpool + jb.i[7];
+  for (int t = threadIdx.x; t < bn; t += PK_THREADS) unit_s[t] = unit[t];
+  __syncthreads();
+  const double* width = cx.dpool + jb.i[8];
+  const double* src = cx.W + jb.i[9] + (long long)b * jb.i[10];
+  const double* lam = cx.LAM + (long long)b * cx.m + jb.i[2];
+  double* out = cx.OUT + (long long)b * cx.n_out + jb.i[0];
+  const bool use_lam = jb.flags & PK_F_LAM;
+  const double sign = jb.f[0];
+  const long long count = jb.i[1];
+  const unsigned e0 = (unsigned)blk_chunk[blockIdx.x] * PK_CHUNK + threadIdx.x;
+  const int step = (int)jb.i[5];
+  const long long c0 = jb.i[6];
+#pragma unroll
+  for (int it = 0; it < PK_ITEMS; ++it) {
+    const unsigned e = e0 + it * PK_THREADS;  // consecutive threads -> consecutive slots
+    if (e >= count) break;
+    const unsigned K = e / (unsigned)bn;
+    const unsigned rem = e - K * (unsigned)bn;
+    const unsigned r = rem / (unsigned)n;
+    const unsigned cc = rem - r * (unsigned)n;
+    double v = sign * ((unit_s[rem] * width[K]) / 2.0);
+    if (use_lam) v = v * lam[K * rows + r];
+    out[e] = v * src[c0 + (long long)K * step + cc];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pk_list_at(const PkCtx& cx, const double* Sb, int b, int scalar, int unit,
+                                             long long src, long long lm, long long c_lo, long long k) {
+  if (unit) return 1.0;
+  if (scalar) return Sb[src];
+  return cx.W[src + (long long)b * lm + c_lo + k];
+}
+
+__global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk_job* __restrict__ jobs,
+                                                             const int* __restrict__ blk_job,
+                                                             const int* __restrict__ blk_chunk) {
+  const pk_job& jb = jobs[blk_job[blockIdx.x]];
+  const int b = blockIdx.y;
+  const double* Sb = cx.S + (long long)b * cx.n_scalar;
+  const double* lam = cx.LAM + (long long)b * cx.m;
+  double* out = cx.OUT + (long long)b * cx.n_out + jb.i[0];
+  const long long count = jb.i[1];
+  const double sign = jb.f[0];
+  const bool use_lam = jb.flags & PK_F_LAM;
+  const double sysv = jb.i[3] >= 0 ? Sb[jb.i[3]] : 1.0;
+  double post = 1.0;
+  if (jb.i[4] == 1) post = cx.SIG[b];
+  if (jb.i[4] == 2) post = lam[jb.i[5]];
+  const long long e0 = (long long)blk_chunk[blockIdx.x] * PK_CHUNK + threadIdx.x;
+  for (int it = 0; it < PK_ITEMS; ++it) {
+    const long long e = e0 + (long long)it * PK_THREADS;
+    if (e >= count) break;
+    double v;
+    switch (jb.type) {
+      case PK_JOB_CONST:
+        v = cx.dpool[jb.i[6] + e];
+        break;
+      case PK_JOB_KRON: {
+        const long long nb = jb.i[7];
+        const long long a = e / nb, q = e - a * nb;
+        double d = cx.dpool[jb.i[6] + a];
+        if (use_lam) d = d * lam[cx.ipool[jb.i[9] + a]];
+        v = sign * (d * Sb[jb.i[8] + q]);
+      } break;
+      case PK_JOB_EXPAND_TABLE: {
+        double d = sign * cx.dpool[jb.i[8] + e];
+        if (use_lam) d = d * lam[jb.i[2] + cx.ipool[jb.i[6] + e]];
+        v = d * cx.W[jb.i[9] + (long long)b * jb.i[10] + cx.ipool[jb.i[7] + e]];
+      } break;
+      case PK_JOB_SCALED:
+        v = pk_list_at(cx, Sb, b, jb.flags & PK_F_A_SCALAR, 0, jb.i[6], jb.i[7], jb.i[8], e) * sysv;
+        if (jb.i[4]) v = v * post;
+        break;
+      case PK_JOB_SYS:
+        v = sysv;
+        if (jb.i[4]) v = v * post;
+        break;
+      default: {  // OUTER / TRIL
+        long long ia, ib;
+        if (jb.type == PK_JOB_OUTER) {
+          ia = e / jb.i[12];
+          ib = e - ia * jb.i[12];
+        } else {
+          ia = (long long)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+          while (ia * (ia + 1) / 2 > e) --ia;
+          while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
+          ib = e - ia * (ia + 1) / 2;
+        }
+        const double va = pk_list_at(cx, Sb, b, jb.flags & PK_F_A_SCALAR, jb.flags & PK_F_A_UNIT, jb.i[6], jb.i[7], jb.i[8], ia);
+        const double vb = pk_list_at(cx, Sb, b, jb.flags & PK_F_B_SCALAR, jb.flags & PK_F_B_UNIT, jb.i[9], jb.i[10], jb.i[11], ib);
+        v = (va * vb) * sysv;
+        if (jb.i[4]) v = v * post;
+      }
+    }
+    out[e] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient: each output column sums its contributions in list order (np.add.at semantics)
+__global__ void __launch_bounds__(PK_THREADS) pk_grad_range(PkCtx cx, const pk_job* __restrict__ jobs, int B) {
+  const pk_job& jb = jobs[blockIdx.y];
+  const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
+  if (gid >= jb.i[1] * B) return;
+  const int b = (int)(gid / jb.i[1]);
+  const long long e = gid - (long long)b * jb.i[1];
+  const double* Sb = cx.S + (long long)b * cx.n_scalar;
+  const long long* q = cx.ipool + jb.i[2];
+  double acc = 0.0;
+  for (long long n = 0; n < jb.i[3]; ++n, q += 4)
+    acc += cx.W[q[0] + (long long)b * q[1] + q[2] + e] * Sb[q[3]];
+  cx.OUT[(long long)b * cx.n_out + jb.i[0] + e] = acc;
+}
+
+__global__ void __launch_bounds__(PK_THREADS) pk_grad_scalar(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
+  const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
+  if (gid >= (long long)n_jobs * B) return;
+  const int j = (int)(gid % n_jobs), b = (int)(gid / n_jobs);
+  const pk_job& jb = jobs[j];
+  const double* Sb = cx.S + (long long)b * cx.n_scalar;
+  const long long* q = cx.ipool + jb.i[2];
+  double acc = 0.0;
+  for (long long n = 0; n < jb.i[3]; ++n, q += 2) acc += (q[0] >= 0 ? Sb[q[0]] * Sb[q[1]] : Sb[q[1]]);
+  cx.OUT[(long long)b * cx.n_out + jb.i[0]] = acc;
+}
+
+// L2 flush helper for timing hygiene
+__global__ void pk_fill(double* p, long long n, double v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}

@@ -1,0 +1,735 @@
+"""Device plan: turns a :class:`~pockit_b200.system.SystemLowering` into what the
+C-ABI engine consumes -- CUDA C for the per-node programs, job records for the
+hand-written kernels, constant pools and the scalar / node-table layouts.
+
+Nothing here depends on the mesh *size* except numbers stored in tables, so a
+re-meshed problem re-uses the generated source verbatim (and the engine's
+cubin cache): sizes, offsets and slot bases reach the kernels through a
+``__constant__`` table indexed by literals.
+
+Data layout in HBM (per engine, ``B`` instances)::
+
+    X      [B][L]        optimisation vectors                 (input)
+    LAM    [B][m]        constraint multipliers, SIG [B]      (input, Hessian only)
+    OUT    [B][n_out]    objective / gradient / constraints / Jacobian values / Hessian values
+    S      [B][n_scalar] scalar table: dt, substituted boundary values, front/back/basic list
+                         values, reduction results, system-level derivative leaves
+    W      rows of [B][L_m(phase)]  node table: one row per per-node list that is later expanded
+                         through the integration operator, reduced, or scaled
+    pools  double / int64 constants: integration blocks, triplets, mesh fractions, weights
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import sympy as sp
+
+from .chain import Leaf, Prod, Term
+from .emit import PRELUDE, CExpr, emit_block
+from .phase import BcType, Segment
+from .system import SysList, SysSegment, SystemLowering
+
+MODES = ("objective", "constraints", "gradient", "jacobian", "hessian")
+OBJ, CONS, GRAD, JAC, HESS = range(5)
+ST_REDUCE, ST_DEFECT, ST_GENERIC, ST_EXPAND, ST_GRAD_RANGE, ST_GRAD_SCALAR = range(6)
+J_CONST, J_KRON, J_EXPAND_TABLE, J_SCALED, J_SYS, J_OUTER, J_TRIL = range(7)
+F_A_SCALAR, F_B_SCALAR, F_A_UNIT, F_B_UNIT, F_LAM = 1, 2, 4, 8, 16
+
+JOB_DTYPE = np.dtype([("type", "<i4"), ("flags", "<i4"), ("i", "<i8", (16,)), ("f", "<f8", (2,))])
+
+NODE_BLOCK = 128
+
+
+class Pools:
+    """Append-only constant pools with de-duplication of identical arrays."""
+
+    def __init__(self):
+        self.d: list[np.ndarray] = []
+        self.i: list[np.ndarray] = []
+        self.nd = 0
+        self.ni = 0
+        self._seen = {}
+
+    def _add(self, arr, kind):
+        arr = np.ascontiguousarray(arr, dtype=np.float64 if kind == "d" else np.int64)
+        key = (kind, arr.shape, arr.tobytes())
+        if key in self._seen:
+            return self._seen[key]
+        if kind == "d":
+            off = self.nd
+            self.d.append(arr)
+            self.nd += arr.size
+        else:
+            off = self.ni
+            self.i.append(arr)
+            self.ni += arr.size
+        self._seen[key] = off
+        return off
+
+    def dbl(self, arr) -> int:
+        return self._add(arr, "d")
+
+    def int(self, arr) -> int:
+        return self._add(arr, "i")
+
+    def arrays(self):
+        d = np.concatenate(self.d) if self.d else np.zeros(1)
+        i = np.concatenate(self.i) if self.i else np.zeros(1, dtype=np.int64)
+        return np.ascontiguousarray(d), np.ascontiguousarray(i)
+
+
+def _ident(leaf: Leaf) -> str:
+    return leaf.kind + "_" + "_".join(str(k) for k in leaf.key) if leaf.key else leaf.kind
+
+
+def term_code(t: Term, weight: bool = False) -> str:
+    """C expression of a product tree, multiplied in the reference's association."""
+
+    def walk(tree):
+        if isinstance(tree, Leaf):
+            return _ident(tree)
+        return f"({walk(tree.left)} * {walk(tree.right)})"
+
+    body = "1.0" if t.tree is None else walk(t.tree)
+    if t.coef == -1.0:
+        body = f"(-{body})"
+    elif t.coef != 1.0:
+        body = f"({body} * {t.coef!r})"
+    return f"({body} * wq)" if weight else body
+
+
+@dataclass
+class PhaseProgram:
+    """Everything one phase's per-node kernel has to compute in one mode."""
+
+    need: set = field(default_factory=set)  # function leaves (kind, fam, i, k)
+    s_store: dict = field(default_factory=dict)  # (nset, code) -> scalar slot
+    w_store: dict = field(default_factory=dict)  # (nset, code) -> table row id
+    direct: list = field(default_factory=list)  # (nset, code, dst, lam or -1, c_lo)
+
+
+class ModePlan:
+    """Plan of one callback."""
+
+    def __init__(self, owner: "DevicePlan", mode: int):
+        self.owner, self.mode = owner, mode
+        lo = owner.lo
+        self.prog = [PhaseProgram() for _ in lo.phases]
+        self.sys_need: dict = {}  # sys Leaf -> scalar slot
+        self.jobs = {s: [] for s in range(6)}
+        self.rows: list[int] = []  # phase of every table row
+        self.n_scalar = owner.header_slots
+        self.table: list[int] = []  # __constant__ table entries
+        self.int_needed = [np.zeros(p.n_I, dtype=bool) for p in lo.phases]
+        self.n_out = 0
+        self.src = None
+        self._build()
+
+    # ---------------------------------------------------------------- allocation helpers
+    def tab(self, value) -> int:
+        if isinstance(value, tuple):  # ('row', r): base of a node-table row
+            value = self.row_base(value[1])
+        self.table.append(int(value))
+        return len(self.table) - 1
+
+    def row_base(self, r: int) -> int:
+        lo, B = self.owner.lo, self.owner.B
+        return sum(B * lo.phases[ph].L_m for ph in self.rows[:r])
+
+    @property
+    def n_table(self) -> int:
+        return self.row_base(len(self.rows))
+
+    @property
+    def n_scalar_final(self) -> int:
+        return self.n_scalar
+
+    def new_row(self, phase: int) -> int:
+        self.rows.append(phase)
+        return len(self.rows) - 1
+
+    def new_slot(self, n: int = 1) -> int:
+        s = self.n_scalar
+        self.n_scalar += n
+        return s
+
+    def _track(self, pi: int, t: Term):
+        for lf in t.leaves():
+            if lf.kind in ("F", "G", "H"):
+                self.prog[pi].need.add(lf)
+
+    def scalar_of(self, pi: int, nset: str, t: Term, weight=False) -> int:
+        """Scalar-table slot holding ``t`` evaluated at the front / back node (or a
+        function of ``s`` only for the 'basic' set)."""
+        self._track(pi, t)
+        key = (nset, term_code(t, weight))
+        store = self.prog[pi].s_store
+        if key not in store:
+            store[key] = self.new_slot()
+        return store[key]
+
+    def row_of(self, pi: int, nset: str, t: Term, weight=False) -> int:
+        self._track(pi, t)
+        key = (nset, term_code(t, weight))
+        store = self.prog[pi].w_store
+        if key not in store:
+            store[key] = self.new_row(pi)
+        return store[key]
+
+    def sys_slot(self, t: Term) -> int:
+        (lf,) = t.leaves()
+        if lf not in self.sys_need:
+            self.sys_need[lf] = self.new_slot()
+        return self.sys_need[lf]
+
+    def job(self, stage: int, typ: int = 0, flags: int = 0, f0: float = 1.0, **iv) -> dict:
+        rec = {"type": typ, "flags": flags, "i": [0] * 16, "f": [f0, 0.0], "rows": {}}
+        for k, v in iv.items():
+            idx = int(k[1:])
+            if isinstance(v, tuple) and v[0] == "row":  # table-row base, resolved once B is known
+                rec["rows"][idx] = v[1]
+            else:
+                rec["i"][idx] = int(v)
+        self.jobs[stage].append(rec)
+        return rec
+
+    # ---------------------------------------------------------------- build per mode
+    def _build(self):
+        lo = self.owner.lo
+        mode = self.mode
+        if mode == OBJ:
+            self.n_out = 1
+            self._need_system_value(lo.F_o, "o", lo.which_o)
+        elif mode == CONS:
+            self.n_out = lo.m
+            for i, fn in enumerate(lo.F_c):
+                self.sys_need[Leaf("sF", ("c", i))] = -1 - i  # written straight to the output
+            self._need_integrals(lo.which_c)
+            self._constraints()
+        elif mode == GRAD:
+            self.n_out = lo.r_s
+            self._need_integrals(lo.which_o)
+            self._gradient()
+        elif mode == JAC:
+            self.n_out = lo.nnz_jac
+            self._need_integrals(lo.which_c)
+            self._slots(lo.jac_segments)
+        else:
+            self.n_out = lo.nnz_hess_o + lo.nnz_hess_c
+            self._need_integrals([a | b for a, b in zip(lo.which_o, lo.which_c)])
+            self._slots(lo.hess_o_segments + lo.hess_c_segments)
+        self._integral_rows()
+
+    def _need_system_value(self, fn, tag, which):
+        self.sys_need[Leaf("sF", (tag,))] = -1
+        self._need_integrals(which)
+
+    def _need_integrals(self, which):
+        for pi, w in enumerate(which):
+            self.int_needed[pi] |= w
+
+    def _integral_rows(self):
+        """Quadrature: ``I_k = dt * sum_c w_c g_k(c)`` (phasebase.py:997-1006).  The node
+        program stores ``g_k(c) * w_c`` in a table row, a REDUCE job sums it."""
+        lo = self.owner.lo
+        self.int_sum_slot = {}
+        for pi, p in enumerate(lo.phases):
+            for k in range(p.n_I):
+                if self.int_needed[pi][k]:
+                    t = Term(Leaf("F", ("I", k)))
+                    self._track(pi, t)
+                    row = self.new_row(pi)
+                    self.prog[pi].w_store[("all", term_code(t, True))] = row
+                    slot = self.new_slot()
+                    self.int_sum_slot[(pi, k)] = slot
+                    self.job(ST_REDUCE, i0=("row", row), i1=p.L_m, i2=0, i3=p.L_m, i4=slot)
+
+    # -- constraints: defects + path values
+    def _constraints(self):
+        lo, own = self.owner.lo, self.owner
+        for pi, p in enumerate(lo.phases):
+            col = p.col
+            base = lo.con_base[pi]
+            fd_rows = []
+            for i in range(p.n_x):
+                t = Term(Leaf("F", ("d", i)))
+                self._track(pi, t)
+                row = self.new_row(pi)
+                self.prog[pi].w_store[("all", term_code(t))] = row
+                fd_rows.append(row)
+            if p.n_x:
+                d = own.defect_tables[pi]
+                self.job(
+                    ST_DEFECT, i0=lo.l_p[pi], i1=col.L_x, i2=col.L_m, i3=p.n_x, i4=col.n_rows,
+                    i5=d["row_ptr"], i6=d["col"], i7=d["data"], i8=d["tpos"], i9=d["tneg"],
+                    i10=("row", fd_rows[0]), i11=own.header[pi], i12=base,
+                )
+            pbase = base + col.n_rows * p.n_x
+            for q in range(p.n_c):
+                t = Term(Leaf("F", ("c", q)))
+                self._track(pi, t)
+                self.prog[pi].direct.append(("all", term_code(t), pbase + q * col.L_m, -1, 0))
+
+    # -- gradient: gather-sum of the objective's lists (systembase.py:646-657)
+    def _gradient(self):
+        lo = self.owner.lo
+        ranges: dict = {}
+        scalars: dict = {}
+        for sg in lo.grad_segments:
+            g = self.sys_slot(sg.sys)
+            if sg.kind == "sys":
+                scalars.setdefault(int(sg.cols[0]), []).append((-1, g))
+                continue
+            pi, p = sg.phase, lo.phases[sg.phase]
+            if sg.nset != "mid":
+                scalars.setdefault(int(sg.cols[0]), []).append((self.scalar_of(pi, sg.nset, sg.term, True), g))
+                continue
+            row = self.row_of(pi, "mid", sg.term, True)
+            c_lo = lo.low[pi].mid_lo
+            if sg.count > 1 and sg.cols[0] == sg.cols[-1]:  # broadcast column: np.add.at accumulates
+                slot = self.new_slot()
+                self.job(ST_REDUCE, i0=("row", row), i1=p.L_m, i2=c_lo, i3=c_lo + sg.count, i4=slot)
+                scalars.setdefault(int(sg.cols[0]), []).append((slot, g))
+            else:
+                ranges.setdefault((int(sg.cols[0]), sg.count), []).append((("row", row), p.L_m, c_lo, g))
+        pools = self.owner.pools
+        for (dst, count), contrib in ranges.items():
+            flat = []
+            rec_rows = {}
+            for n, (row, lm, c_lo, g) in enumerate(contrib):
+                rec_rows[n] = row[1]
+                flat += [0, lm, c_lo, g]
+            rec = self.job(ST_GRAD_RANGE, i0=dst, i1=count, i3=len(contrib))
+            rec["contrib"] = (flat, rec_rows)  # table-row bases are patched in at finalisation
+        for dst, contrib in scalars.items():
+            flat = [v for pair in contrib for v in pair]
+            self.job(ST_GRAD_SCALAR, i0=dst, i2=pools.int(flat), i3=len(contrib))
+
+    # -- Jacobian / Hessian slot runs
+    def _post(self, sg: SysSegment):
+        if sg.post is None:
+            return 0, 0
+        if sg.post[0] == "sigma":
+            return 1, 0
+        return 2, sg.post[1]
+
+    def _slots(self, segs: list[SysSegment]):
+        lo, own = self.owner.lo, self.owner
+        dst = 0
+        for sg in segs:
+            if sg.kind == "phase":
+                self._phase_run(sg, dst)
+            elif sg.kind == "sys":
+                pk, pi_ = self._post(sg)
+                self.job(ST_GENERIC, J_SYS, i0=dst, i1=1, i2=-1, i3=self.sys_slot(sg.sys), i4=pk, i5=pi_)
+            elif sg.kind == "scaled":
+                pk, pi_ = self._post(sg)
+                pi, p = sg.phase, lo.phases[sg.phase]
+                if sg.nset == "mid":
+                    row = self.row_of(pi, "mid", sg.term, True)
+                    self.job(
+                        ST_GENERIC, J_SCALED, i0=dst, i1=sg.count, i2=-1, i3=self.sys_slot(sg.sys), i4=pk, i5=pi_,
+                        i6=("row", row), i7=p.L_m, i8=lo.low[pi].mid_lo,
+                    )
+                else:
+                    slot = self.scalar_of(pi, sg.nset, sg.term, True)
+                    self.job(
+                        ST_GENERIC, J_SCALED, F_A_SCALAR, i0=dst, i1=1, i2=-1, i3=self.sys_slot(sg.sys),
+                        i4=pk, i5=pi_, i6=slot,
+                    )
+            else:  # outer / tril
+                pk, pi_ = self._post(sg)
+                a, b = sg.pair
+                fa, ia = self._list_source(a)
+                fb, ib = self._list_source(b)
+                flags = {0: 0, 1: F_A_SCALAR, 2: F_A_UNIT}[fa] | {0: 0, 1: F_B_SCALAR, 2: F_B_UNIT}[fb]
+                self.job(
+                    ST_GENERIC, J_OUTER if sg.kind == "outer" else J_TRIL, flags, i0=dst, i1=sg.count, i2=-1,
+                    i3=self.sys_slot(sg.sys), i4=pk, i5=pi_, i6=ia[0], i7=ia[1], i8=ia[2],
+                    i9=ib[0], i10=ib[1], i11=ib[2], i12=b.count,
+                )
+            dst += sg.count
+
+    def _list_source(self, sl: SysList):
+        """(flag bits, (source, L_m, c_lo)); flag 1 = scalar slot, 2 = the constant 1."""
+        lo = self.owner.lo
+        if sl.term is None:
+            return 2, (0, 0, 0)
+        pi, p = sl.phase, lo.phases[sl.phase]
+        if sl.nset != "mid":
+            return 1, (self.scalar_of(pi, sl.nset, sl.term, True), 0, 0)
+        row = self.row_of(pi, "mid", sl.term, True)
+        c_lo = lo.low[pi].mid_lo
+        if sl.summed:
+            key = ("sum", pi, row)
+            if key not in self.prog[pi].s_store:
+                slot = self.new_slot()
+                self.prog[pi].s_store[key] = slot
+                self.job(ST_REDUCE, i0=("row", row), i1=p.L_m, i2=c_lo, i3=c_lo + lo.low[pi].n_mid, i4=slot)
+            return 1, (self.prog[pi].s_store[key], 0, 0)
+        return 0, (("row", row), p.L_m, c_lo)
+
+    def _phase_run(self, sg: SysSegment, dst: int):
+        lo, own = self.owner.lo, self.owner
+        seg: Segment = sg.seg
+        pi, p = sg.phase, lo.phases[sg.phase]
+        col = p.col
+        pools = own.pools
+        has_lam = self.mode == HESS
+        if seg.kind == "const":
+            self.job(ST_GENERIC, J_CONST, i0=dst, i1=seg.count, i2=-1, i3=-1, i6=pools.dbl(seg.data))
+        elif seg.kind == "kron":
+            nb = len(seg.terms)
+            first = self.new_slot(nb)
+            for n, t in enumerate(seg.terms):
+                self._track(pi, t)
+                self.prog[pi].s_store[(seg.nset, term_code(t), first + n)] = first + n
+            flags = F_LAM if has_lam else 0
+            rows_off = pools.int(seg.lam_rows + sg.lam_base) if has_lam else 0
+            self.job(
+                ST_GENERIC, J_KRON, flags, f0=seg.sign, i0=dst, i1=seg.count, i2=-1, i3=-1,
+                i6=pools.dbl(seg.data), i7=nb, i8=first, i9=rows_off,
+            )
+        elif seg.kind == "expand":
+            row = self.row_of(pi, "mid", seg.terms[0])
+            lam = sg.lam_base + seg.lam_off if has_lam else -1
+            for piece in own.expand_pieces[pi]:
+                if piece["kind"] == "table":
+                    self.job(
+                        ST_GENERIC, J_EXPAND_TABLE, F_LAM if has_lam else 0, f0=seg.sign,
+                        i0=dst + piece["k0"], i1=piece["count"], i2=lam, i3=-1,
+                        i6=piece["row"], i7=piece["col"], i8=piece["data"], i9=("row", row), i10=col.L_m,
+                    )
+                else:
+                    self.job(
+                        ST_EXPAND, 0, F_LAM if has_lam else 0, f0=seg.sign,
+                        i0=dst + piece["k0"], i1=piece["count"], i2=(lam + piece["row0"]) if has_lam else -1,
+                        i3=piece["n"], i4=piece["rows"], i5=piece["step"], i6=piece["c0"],
+                        i7=piece["unit"], i8=piece["width"], i9=("row", row), i10=col.L_m,
+                    )
+        else:  # direct
+            lam = sg.lam_base + seg.lam_off if has_lam else -1
+            t = seg.terms[0]
+            self._track(pi, t)
+            c_lo = {"front": 0, "mid": lo.low[pi].mid_lo, "back": col.L_m - 1}[seg.nset]
+            self.prog[pi].direct.append((seg.nset, term_code(t), dst, lam, c_lo))
+
+
+class DevicePlan:
+    """Pools + per-mode plans for one lowered system."""
+
+    def __init__(self, lo: SystemLowering, batch: int = 1, fastmath: bool = False):
+        self.lo = lo
+        self.B = int(batch)
+        self.fastmath = fastmath
+        self.pools = Pools()
+        # scalar-table header: per phase [dt, front values (n_x), back values (n_x)]
+        self.header = []
+        off = 0
+        for p in lo.phases:
+            self.header.append(off)
+            off += 1 + 2 * p.n_x
+        self.header_slots = off
+        # FIXED boundary values, per instance: per phase [x0 (n_x), xf (n_x), t0, tf]
+        self.fix_off = []
+        fix = []
+        for p in lo.phases:
+            self.fix_off.append(len(fix))
+            for info in list(p.info_bc_0) + list(p.info_bc_f) + [p.info_t_0, p.info_t_f]:
+                fix.append(float(info.v) if info.t == BcType.FIXED else 0.0)
+        self.fixed_default = np.array(fix, dtype=np.float64)
+        self.n_fixed = len(fix)
+        # mesh tables
+        self.tm_off = [self.pools.dbl(p.col.t_m) for p in lo.phases]
+        self.wm_off = [self.pools.dbl(p.col.w_m) for p in lo.phases]
+        self.defect_tables = [self._defect_tables(p) for p in lo.phases]
+        self.expand_pieces = [self._expand_pieces(p) for p in lo.phases]
+        self.modes: dict[int, ModePlan] = {}
+
+    def mode(self, m: int) -> ModePlan:
+        if m not in self.modes:
+            self.modes[m] = ModePlan(self, m)
+        return self.modes[m]
+
+    # ---------------------------------------------------------------- constant tables
+    def _defect_tables(self, p):
+        col = p.col
+        T, I = col.T, col.I
+        rows = np.concatenate([I.f.row, I.m.row, I.b.row]).astype(np.int64)
+        cols = np.concatenate([I.f.col, I.m.col, I.b.col]).astype(np.int64)
+        data = np.concatenate([I.f.data, I.m.data, I.b.data])
+        order = np.concatenate([I.f.k, I.m.k, I.b.k]).argsort(kind="stable")
+        rows, cols, data = rows[order], cols[order], data[order]
+        row_ptr = np.searchsorted(rows, np.arange(col.n_rows + 1))
+        trow = np.concatenate([T.f.row, T.m.row, T.b.row]).astype(np.int64)
+        tcol = np.concatenate([T.f.col, T.m.col, T.b.col]).astype(np.int64)
+        tval = np.concatenate([T.f.data, T.m.data, T.b.data])
+        tpos = np.zeros(col.n_rows, dtype=np.int64)
+        tneg = np.zeros(col.n_rows, dtype=np.int64)
+        tpos[trow[tval > 0]] = tcol[tval > 0]
+        tneg[trow[tval < 0]] = tcol[tval < 0]
+        P = self.pools
+        return dict(row_ptr=P.int(row_ptr), col=P.int(cols), data=P.dbl(data), tpos=P.int(tpos), tneg=P.int(tneg))
+
+    def _expand_pieces(self, p):
+        """Split the middle part of the integration operator into runs the EXPAND
+        kernel can address arithmetically (interior intervals of a mesh whose
+        intervals all have the same order) and table-driven remainders."""
+        col = p.col
+        Im = col.I.m
+        P = self.pools
+        nK = len(col.num_point)
+        n = int(col.num_point[0])
+        rows = n - 1 if col.scheme == "lgl" else n
+        table = lambda k0, k1: dict(
+            kind="table", k0=k0, count=k1 - k0, row=P.int(Im.row[k0:k1]), col=P.int(Im.col[k0:k1]),
+            data=P.dbl(Im.data[k0:k1]),
+        )
+        if not (col.same_order and col.dense_blocks and nK >= 3):
+            return [table(0, len(Im))] if len(Im) else []
+        bn = rows * n
+        # first interval loses its front column, the last one (LGL) its back column
+        head = int(np.searchsorted(Im.row, rows))  # triplets of interval 0
+        tail0 = int(np.searchsorted(Im.row, rows * (nK - 1)))
+        assert tail0 - head == bn * (nK - 2)
+        from .discretization import _unit_integration_block
+
+        unit = _unit_integration_block(col.scheme, n)
+        step = n - 1 if col.scheme == "lgl" else n
+        pieces = [table(0, head)]
+        pieces.append(
+            dict(
+                kind="block", k0=head, count=tail0 - head, n=n, rows=rows, step=step, c0=int(col.l_m[1]),
+                row0=rows, unit=P.dbl(unit.ravel()), width=P.dbl(col.width) + 1,
+            )
+        )
+        pieces.append(table(tail0, len(Im)))
+        return [q for q in pieces if q["count"]]
+
+    # ---------------------------------------------------------------- code generation
+    def source(self, m: int) -> tuple[str, list[str], Optional[str]]:
+        """CUDA C of mode ``m``: (source, node kernel names, system kernel name or None)."""
+        mp = self.mode(m)
+        if mp.src is not None:
+            return mp.src
+        lo = self.lo
+        name = MODES[m]
+        body, kernels = [], []
+        for pi in range(len(lo.phases)):
+            kname = f"pk_node_{name}_p{pi}"
+            body.append(self._node_kernel(mp, pi, kname))
+            kernels.append(kname)
+        sys_name = None
+        if mp.sys_need or any(w.any() for w in mp.int_needed):
+            sys_name = f"pk_sys_{name}"
+            body.append(self._sys_kernel(mp, sys_name))
+        head = [
+            "// generated by pockit_b200.plan -- per-node programs of mode '%s'" % name,
+            PRELUDE,
+            f"__constant__ long long pk_tab_{name}[{max(1, len(mp.table))}];",
+        ]
+        mp.src = ("\n".join(head + body) + "\n", kernels, sys_name)
+        return mp.src
+
+    def finalize(self, m: int) -> dict:
+        """Everything the engine needs for mode ``m`` (call after all modes were
+        built so the pools are complete): source, table, resolved job arrays."""
+        mp = self.mode(m)
+        src, kernels, sys_name = self.source(m)
+        jobs = {}
+        for stage, recs in mp.jobs.items():
+            arr = np.zeros(len(recs), dtype=JOB_DTYPE)
+            for n, rec in enumerate(recs):
+                iv = list(rec["i"])
+                for idx, row in rec["rows"].items():
+                    iv[idx] = mp.row_base(row)
+                if "contrib" in rec:
+                    flat, rows = rec["contrib"]
+                    flat = list(flat)
+                    for cn, row in rows.items():
+                        flat[4 * cn] = mp.row_base(row)
+                    iv[2] = self.pools.int(flat)
+                arr[n] = (rec["type"], rec["flags"], iv, rec["f"])
+            jobs[stage] = arr
+        return dict(
+            source=src, kernels=kernels, sys_kernel=sys_name, table=np.array(mp.table, dtype=np.int64),
+            table_symbol=f"pk_tab_{MODES[m]}", jobs=jobs, n_scalar=mp.n_scalar, n_out=mp.n_out,
+            n_table=mp.n_table,
+        )
+
+    def _node_kernel(self, mp: ModePlan, pi: int, kname: str) -> str:
+        lo = self.lo
+        p = lo.phases[pi]
+        col = p.col
+        prog = mp.prog[pi]
+        name = MODES[mp.mode]
+        T = lambda v: f"T[{mp.tab(v)}]"
+        has_back = col.index_mstage.b
+        n_x, n_u, n_s = p.n_x, p.n_u, p.n_s
+        L = []
+        A = L.append
+        A(f'extern "C" __global__ void __launch_bounds__({NODE_BLOCK}) {kname}(')
+        A("    const double* __restrict__ X, const double* __restrict__ LAM, const double* __restrict__ FIX,")
+        A("    const double* __restrict__ TM, const double* __restrict__ WM,")
+        A("    double* __restrict__ S, double* __restrict__ W, double* __restrict__ OUT, int B)")
+        A("{")
+        A(f"    const long long* T = pk_tab_{name};")
+        A(f"    const int Lm = (int){T(col.L_m)};")
+        A("    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;")
+        A("    if (gid >= (long long)B * Lm) return;")
+        A("    const int b = (int)(gid / Lm);")
+        A("    const int c = (int)(gid - (long long)b * Lm);")
+        A(f"    const double* xs = X + (long long)b * {T(lo.r_s)};")
+        A(f"    const double* xp = xs + {T(lo.l_p[pi])};")
+        A(f"    const double* sv = xs + {T(lo.l_s)};")
+        A(f"    double* Sb = S + (long long)b * {T(mp.n_scalar_final)};")
+        A(f"    const double* lam = LAM + (long long)b * {T(lo.m)};")
+        A(f"    double* out = OUT + (long long)b * {T(mp.n_out)};")
+        A(f"    const double* fix = FIX + (long long)b * {T(self.n_fixed)} + {T(self.fix_off[pi])};")
+        A(f"    const int Lx = (int){T(col.L_x)};")
+        A("    const bool first = (c == 0), last = (c == Lm - 1);")
+        names = {}
+        for k, sym in enumerate(p.s):
+            A(f"    const double s{k} = sv[{k}];")
+            names[sym] = f"s{k}"
+        # boundary functions of s: values and derivative leaves
+        bnd = []
+        infos = (
+            [(("x0", i), p.info_bc_0[i]) for i in range(n_x)]
+            + [(("xf", i), p.info_bc_f[i]) for i in range(n_x)]
+            + [(("t0",), p.info_t_0), (("tf",), p.info_t_f)]
+        )
+        for tag, info in infos:
+            if info.t == BcType.FUNC:
+                tg = "_".join(str(v) for v in tag)
+                bnd.append((f"bV_{tg}", info.v.expr))
+                bnd += [(f"bG_{tg}_{jj}", e) for jj, e in enumerate(info.v.G_expr)]
+                bnd += [(f"bH_{tg}_{jj}", e) for jj, e in enumerate(info.v.H_expr)]
+        if bnd:
+            L.append(emit_block(bnd, names, prefix="cb").rstrip("\n"))
+
+        def bc_value(tag, info, free_expr, fix_index):
+            if info.t == BcType.FREE:
+                return free_expr
+            if info.t == BcType.FIXED:
+                return f"fix[{fix_index}]"
+            return "bV_" + "_".join(str(v) for v in tag)
+
+        A(f"    const double t0 = {bc_value(('t0',), p.info_t_0, f'xp[{T(col.L - 2)}]', 2 * n_x)};")
+        A(f"    const double tf = {bc_value(('tf',), p.info_t_f, f'xp[{T(col.L - 1)}]', 2 * n_x + 1)};")
+        A("    const double dt = tf - t0;")
+        A("    const double mt = (tf + t0) / 2.0;")
+        A("    const double tm = TM[c];")
+        A("    const double om = 1.0 - tm;")
+        A("    const double wq = WM[c];")
+        A("    const double t = (tm - 0.5) * dt + mt;")
+        names[p.t] = "t"
+        for i, sym in enumerate(p.x):
+            A(f"    double x{i} = xp[{i}LL * Lx + c];")
+            if p.info_bc_0[i].t != BcType.FREE:
+                A(f"    if (first) x{i} = {bc_value(('x0', i), p.info_bc_0[i], '', i)};")
+            if has_back and p.info_bc_f[i].t != BcType.FREE:
+                A(f"    if (last) x{i} = {bc_value(('xf', i), p.info_bc_f[i], '', n_x + i)};")
+            names[sym] = f"x{i}"
+        for j, sym in enumerate(p.u):
+            A(f"    const double u{j} = xp[{n_x}LL * Lx + {j}LL * Lm + c];")
+            names[sym] = f"u{j}"
+        # function leaves needed by this mode, one CSE over all of them
+        fam = {"d": p.F_d, "I": p.F_I, "c": p.F_c}
+        leaves = []
+        for lf in sorted(prog.need, key=lambda l: (l.key[0], l.key[1], l.kind, l.key[2:] or (0,))):
+            fn = fam[lf.key[0]][lf.key[1]]
+            e = fn.expr if lf.kind == "F" else (fn.G_expr if lf.kind == "G" else fn.H_expr)[lf.key[2]]
+            leaves.append((_ident(lf), e))
+        if leaves:
+            L.append(emit_block(leaves, names, prefix="ce").rstrip("\n"))
+        A("    const long long nd = (long long)b * Lm + c;")
+
+        def stores(nset, indent):
+            body = []
+            for key, slot in prog.s_store.items():
+                if key[0] == nset:
+                    body.append(f"{indent}Sb[{T(slot)}] = {key[1]};")
+            for key, row in prog.w_store.items():
+                if key[0] == nset:
+                    body.append(f"{indent}W[{T(('row', row))} + nd] = {key[1]};")
+            for ns, code, dst, lam, c_lo in prog.direct:
+                if ns == nset:
+                    e = f"c - {T(c_lo)}"
+                    val = code if lam < 0 else f"{code} * lam[{T(lam)} + {e}]"
+                    body.append(f"{indent}out[{T(dst)} + {e}] = {val};")
+            return body
+
+        L += stores("all", "    ")
+        A("    if (first) {")
+        A(f"        Sb[{T(self.header[pi])}] = dt;")
+        for i in range(n_x):
+            A(f"        Sb[{T(self.header[pi] + 1 + i)}] = x{i};")
+        L += stores("basic", "        ")
+        L += stores("front", "        ")
+        if has_back:
+            A("    } else if (last) {")
+            L += stores("back", "        ")
+        A("    } else {")
+        L += stores("mid", "        ")
+        A("    }")
+        A("    if (last) {")
+        for i in range(n_x):
+            if has_back:
+                A(f"        Sb[{T(self.header[pi] + 1 + n_x + i)}] = x{i};")
+            else:
+                free = f"xp[{i}LL * Lx + Lm]"
+                A(
+                    f"        Sb[{T(self.header[pi] + 1 + n_x + i)}] = "
+                    f"{bc_value(('xf', i), p.info_bc_f[i], free, n_x + i)};"
+                )
+        A("    }")
+        A("}")
+        return "\n".join(L)
+
+    def _sys_kernel(self, mp: ModePlan, kname: str) -> str:
+        lo = self.lo
+        name = MODES[mp.mode]
+        T = lambda v: f"T[{mp.tab(v)}]"
+        L = []
+        A = L.append
+        A(f'extern "C" __global__ void {kname}(')
+        A("    const double* __restrict__ X, double* __restrict__ S, double* __restrict__ OUT, int B)")
+        A("{")
+        A(f"    const long long* T = pk_tab_{name};")
+        A("    const int b = blockIdx.x * blockDim.x + threadIdx.x;")
+        A("    if (b >= B) return;")
+        A(f"    const double* sv = X + (long long)b * {T(lo.r_s)} + {T(lo.l_s)};")
+        A(f"    double* Sb = S + (long long)b * {T(mp.n_scalar_final)};")
+        A(f"    double* out = OUT + (long long)b * {T(mp.n_out)};")
+        names = {}
+        n = 0
+        for pi, p in enumerate(lo.phases):
+            for k, sym in enumerate(p.I):
+                if mp.int_needed[pi][k]:
+                    # vi.dot(w_m) * dt   (phasebase.py:1004)
+                    A(f"    const double I{n} = Sb[{T(mp.int_sum_slot[(pi, k)])}] * Sb[{T(self.header[pi])}];")
+                else:
+                    A(f"    const double I{n} = 0.0;")
+                names[sym] = f"I{n}"
+                n += 1
+        for k, sym in enumerate(lo.system.s):
+            A(f"    const double s{k} = sv[{k}];")
+            names[sym] = f"s{k}"
+        outs = []
+        for lf in mp.sys_need:
+            fn = lo.F_o if lf.key[0] == "o" else lo.F_c[lf.key[1]]
+            idx = lf.key[-1]
+            e = fn.expr if lf.kind == "sF" else (fn.G_expr if lf.kind == "sG" else fn.H_expr)[idx]
+            outs.append((_ident(lf), e))
+        if outs:
+            L.append(emit_block(outs, names, prefix="cs").rstrip("\n"))
+        for lf, slot in mp.sys_need.items():
+            if slot < 0:
+                A(f"    out[{-1 - slot}] = {_ident(lf)};")
+            else:
+                A(f"    Sb[{T(slot)}] = {_ident(lf)};")
+        A("}")
+        return "\n".join(L)
