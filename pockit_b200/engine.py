@@ -1,0 +1,321 @@
+"""ctypes binding of the C-ABI engine (``include/pockit_b200.h``) and the
+host-side glue that feeds it a :class:`~pockit_b200.plan.DevicePlan`.
+
+There is no CPU fallback: if ``libpockit_b200.so`` or a CUDA device is missing
+the constructor raises, and so does every callback of the owning System.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+from . import plan as P
+
+__all__ = ["Engine", "load_library", "library_path", "PinnedArray"]
+
+N_STAGES = 6
+N_MODES = 5
+
+
+class _Job(C.Structure):
+    _fields_ = [("type", C.c_int32), ("flags", C.c_int32), ("i", C.c_int64 * 16), ("f", C.c_double * 2)]
+
+
+class _Dims(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("batch", C.c_int32), ("L", C.c_int64), ("m", C.c_int64),
+        ("nnz_jac", C.c_int64), ("nnz_hess", C.c_int64), ("n_scalar", C.c_int64), ("n_table", C.c_int64),
+        ("n_fixed", C.c_int64),
+    ]
+
+
+class _NodeProgram(C.Structure):
+    _fields_ = [("kernel", C.c_char_p), ("n_nodes", C.c_int64), ("tm_offset", C.c_int64), ("wm_offset", C.c_int64)]
+
+
+class _ModeDesc(C.Structure):
+    _fields_ = [
+        ("cuda_source", C.c_char_p), ("nvrtc_options", C.POINTER(C.c_char_p)), ("n_nvrtc_options", C.c_int32),
+        ("n_node_programs", C.c_int32), ("node_programs", C.POINTER(_NodeProgram)), ("system_kernel", C.c_char_p),
+        ("table_symbol", C.c_char_p), ("table", C.POINTER(C.c_int64)), ("n_table_entries", C.c_int64),
+        ("n_scalar", C.c_int64), ("n_out", C.c_int64), ("jobs", C.c_void_p * N_STAGES), ("n_jobs", C.c_int64 * N_STAGES),
+    ]
+
+
+assert C.sizeof(_Job) == P.JOB_DTYPE.itemsize
+
+_LIB = None
+
+
+def library_path() -> Path:
+    return Path(os.environ.get("POCKIT_B200_LIB", Path(__file__).resolve().parent / "libpockit_b200.so"))
+
+
+def load_library():
+    """Load ``libpockit_b200.so`` (built by ``__graft_entry__.build()``)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not path.exists():
+        raise RuntimeError(f"{path} not found: build the CUDA engine first (python -c 'import __graft_entry__ as g; g.build()')")
+    lib = C.CDLL(str(path))
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p
+    sig = {
+        "pk_abi_version": ([], C.c_int),
+        "pk_last_error": ([], C.c_char_p),
+        "pk_device_count": ([C.POINTER(C.c_int)], C.c_int),
+        "pk_engine_create": ([C.POINTER(_Dims), C.c_int, C.POINTER(vp)], C.c_int),
+        "pk_engine_destroy": ([vp], C.c_int),
+        "pk_engine_set_pools": ([vp, vp, C.c_int64, vp, C.c_int64], C.c_int),
+        "pk_engine_set_fixed": ([vp, vp], C.c_int),
+        "pk_engine_load_mode": ([vp, C.c_int, C.POINTER(_ModeDesc)], C.c_int),
+        "pk_engine_get_cubin": ([vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)], C.c_int),
+        "pk_eval_objective": ([vp, vp, vp], C.c_int),
+        "pk_eval_gradient": ([vp, vp, vp], C.c_int),
+        "pk_eval_constraints": ([vp, vp, vp], C.c_int),
+        "pk_eval_jacobian": ([vp, vp, vp], C.c_int),
+        "pk_eval_hessian": ([vp, vp, vp, vp, vp], C.c_int),
+        "pk_upload_x": ([vp, vp], C.c_int),
+        "pk_upload_multipliers": ([vp, vp, vp], C.c_int),
+        "pk_run": ([vp, C.c_int], C.c_int),
+        "pk_sync": ([vp], C.c_int),
+        "pk_download": ([vp, C.c_int, vp], C.c_int),
+        "pk_time": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
+        "pk_kernel_launches": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "pk_flush_l2": ([vp], C.c_int),
+        "pk_alloc_host": ([C.c_size_t], vp),
+        "pk_free_host": ([vp], None),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, res
+    if lib.pk_abi_version() != 1:
+        raise RuntimeError("libpockit_b200.so: ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray:
+    """float64 NumPy view over page-locked host memory (``pk_alloc_host``)."""
+
+    def __init__(self, n: int):
+        self._lib = load_library()
+        self._p = self._lib.pk_alloc_host(max(8, 8 * int(n)))
+        if not self._p:
+            raise MemoryError("pk_alloc_host failed")
+        self.array = np.ctypeslib.as_array((C.c_double * int(n)).from_address(self._p)) if n else np.zeros(0)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            self._lib.pk_free_host(self._p)
+            self._p = None
+
+
+class Engine:
+    """One CUDA engine for one lowered system (``batch`` independent instances)."""
+
+    def __init__(self, lowering, batch: int = 1, fastmath: bool = False, device: Optional[int] = None,
+                 fixed: Optional[np.ndarray] = None):
+        self.lib = load_library()
+        self.lowering = lowering
+        self.B = int(batch)
+        self.plan = P.DevicePlan(lowering, self.B, fastmath)
+        self.fin = {}
+        for m in range(N_MODES):
+            self.plan.mode(m)
+        for m in range(N_MODES):
+            self.fin[m] = self.plan.finalize(m)
+        lo = lowering
+        self.n_out = {m: self.fin[m]["n_out"] for m in range(N_MODES)}
+        dims = _Dims(
+            1, self.B, lo.r_s, lo.m, lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c,
+            max(1, max(f["n_scalar"] for f in self.fin.values())),
+            max(1, max(f["n_table"] for f in self.fin.values())), self.plan.n_fixed,
+        )
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("POCKIT_B200_USE_LOCAL_RANK") else 0
+        self.device = device
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.lib.pk_engine_create(C.byref(dims), device, C.byref(h)))
+        self._h = h
+        self._dpool, self._ipool = self.plan.pools.arrays()
+        self._check(self.lib.pk_engine_set_pools(h, _ptr(self._dpool), self._dpool.size, _ptr(self._ipool), self._ipool.size))
+        self.set_fixed(fixed)
+        self._loaded = set()
+        self._opts = ["--fmad=true"] if fastmath else []
+        self._one = np.ones(self.B)
+        self._zero_lam = np.zeros(self.B * max(1, lo.m))
+
+    # ------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError("pockit_b200 engine: " + self.lib.pk_last_error().decode(errors="replace"))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.pk_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_fixed(self, fixed: Optional[np.ndarray]):
+        """FIXED boundary values per instance, ``[batch][n_fixed]`` in the order
+        per phase ``[x(t0) (n_x), x(tf) (n_x), t0, tf]`` (entries of non-FIXED slots are ignored)."""
+        if fixed is None:
+            fixed = np.tile(self.plan.fixed_default, (self.B, 1))
+        fixed = np.ascontiguousarray(np.asarray(fixed, dtype=np.float64).reshape(self.B, self.plan.n_fixed))
+        self._fixed = fixed
+        if fixed.size:
+            self._check(self.lib.pk_engine_set_fixed(self._h, _ptr(fixed)))
+
+    def load(self, mode: int):
+        if mode in self._loaded:
+            return
+        f = self.fin[mode]
+        lo = self.lowering
+        progs = (_NodeProgram * max(1, len(f["kernels"])))()
+        for pi, k in enumerate(f["kernels"]):
+            progs[pi] = _NodeProgram(k.encode(), lo.phases[pi].L_m, self.plan.tm_off[pi], self.plan.wm_off[pi])
+        opts = (C.c_char_p * max(1, len(self._opts)))(*[o.encode() for o in self._opts])
+        table = np.ascontiguousarray(f["table"], dtype=np.int64)
+        d = _ModeDesc()
+        d.cuda_source = f["source"].encode()
+        d.nvrtc_options = opts
+        d.n_nvrtc_options = len(self._opts)
+        d.n_node_programs = len(f["kernels"])
+        d.node_programs = progs
+        d.system_kernel = f["sys_kernel"].encode() if f["sys_kernel"] else None
+        d.table_symbol = f["table_symbol"].encode()
+        d.table = table.ctypes.data_as(C.POINTER(C.c_int64))
+        d.n_table_entries = len(table)
+        d.n_scalar = f["n_scalar"]
+        d.n_out = f["n_out"]
+        keep = []
+        for s in range(N_STAGES):
+            arr = np.ascontiguousarray(f["jobs"][s])
+            keep.append(arr)
+            d.jobs[s] = arr.ctypes.data if len(arr) else None
+            d.n_jobs[s] = len(arr)
+        self._check(self.lib.pk_engine_load_mode(self._h, mode, C.byref(d)))
+        self._loaded.add(mode)
+
+    # ------------------------------------------------------------------ host-to-host callbacks
+    def _x(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.size != self.B * self.lowering.r_s:
+            raise ValueError(f"x must have {self.B * self.lowering.r_s} entries")
+        return x
+
+    def _out(self, mode: int, out: Optional[np.ndarray]) -> np.ndarray:
+        n = self.B * self.n_out[mode]
+        if out is None:
+            return np.empty(n, dtype=np.float64)
+        if out.size != n or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array of the callback's size")
+        return out
+
+    def _shape(self, mode, out):
+        return out if self.B == 1 else out.reshape(self.B, self.n_out[mode])
+
+    def objective(self, x):
+        self.load(P.OBJ)
+        x, out = self._x(x), self._out(P.OBJ, None)
+        self._check(self.lib.pk_eval_objective(self._h, _ptr(x), _ptr(out)))
+        return np.float64(out[0]) if self.B == 1 else out
+
+    def gradient(self, x, out=None):
+        self.load(P.GRAD)
+        x, out = self._x(x), self._out(P.GRAD, out)
+        self._check(self.lib.pk_eval_gradient(self._h, _ptr(x), _ptr(out)))
+        return self._shape(P.GRAD, out)
+
+    def constraints(self, x, out=None):
+        self.load(P.CONS)
+        x, out = self._x(x), self._out(P.CONS, out)
+        self._check(self.lib.pk_eval_constraints(self._h, _ptr(x), _ptr(out)))
+        return self._shape(P.CONS, out)
+
+    def jacobian(self, x, out=None):
+        self.load(P.JAC)
+        x, out = self._x(x), self._out(P.JAC, out)
+        self._check(self.lib.pk_eval_jacobian(self._h, _ptr(x), _ptr(out)))
+        return self._shape(P.JAC, out)
+
+    def hessian(self, x, fct_c, fct_o, out=None):
+        self.load(P.HESS)
+        x, out = self._x(x), self._out(P.HESS, out)
+        lam = np.ascontiguousarray(fct_c, dtype=np.float64)
+        if lam.size != self.B * self.lowering.m:
+            raise ValueError(f"fct_c must have {self.B * self.lowering.m} entries")
+        sig = np.ascontiguousarray(np.broadcast_to(np.asarray(fct_o, dtype=np.float64), (self.B,)))
+        self._check(self.lib.pk_eval_hessian(self._h, _ptr(x), _ptr(lam), _ptr(sig), _ptr(out)))
+        return self._shape(P.HESS, out)
+
+    def hessian_o(self, x):
+        n_o = self.lowering.nnz_hess_o
+        full = self.hessian(x, self._zero_lam[: self.B * self.lowering.m], self._one)
+        return np.array(full[..., :n_o])
+
+    def hessian_c(self, x, fct_c):
+        n_o = self.lowering.nnz_hess_o
+        full = self.hessian(x, fct_c, np.zeros(self.B))
+        return np.array(full[..., n_o:])
+
+    # ------------------------------------------------------------------ device-resident path
+    def upload(self, x, fct_c=None, fct_o=None):
+        x = self._x(x)
+        self._check(self.lib.pk_upload_x(self._h, _ptr(x)))
+        if fct_c is not None:
+            lam = np.ascontiguousarray(fct_c, dtype=np.float64)
+            sig = np.ascontiguousarray(np.broadcast_to(np.asarray(1.0 if fct_o is None else fct_o, dtype=np.float64), (self.B,)))
+            self._check(self.lib.pk_upload_multipliers(self._h, _ptr(lam), _ptr(sig)))
+        self.sync()
+
+    def run(self, mode: int):
+        self.load(mode)
+        self._check(self.lib.pk_run(self._h, mode))
+
+    def sync(self):
+        self._check(self.lib.pk_sync(self._h))
+
+    def download(self, mode: int, out=None):
+        out = self._out(mode, out)
+        self._check(self.lib.pk_download(self._h, mode, _ptr(out)))
+        return self._shape(mode, out)
+
+    def time(self, mode: int, iters: int = 10, stages: bool = False):
+        """CUDA-event time (ms) of ``iters`` back-to-back runs; optionally per stage."""
+        self.load(mode)
+        total = C.c_float()
+        st = (C.c_float * (N_STAGES + 2))()
+        self._check(self.lib.pk_time(self._h, mode, iters, C.byref(total), st if stages else None))
+        return (total.value, list(st)) if stages else total.value
+
+    def flush_l2(self):
+        self._check(self.lib.pk_flush_l2(self._h))
+
+    @property
+    def launches(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.pk_kernel_launches(self._h, C.byref(n)))
+        return n.value
+
+    def cubin(self, mode: int) -> bytes:
+        self.load(mode)
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.pk_engine_get_cubin(self._h, mode, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
