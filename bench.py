@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the NLP-callback hot path.
+
+A *step* is one callback evaluation set -- objective + gradient + constraints +
+Jacobian values + Hessian-of-Lagrangian values at the same (x, lambda, sigma) --
+of BASELINE.json's configs[1]: robot_arm on the LGR transcription, 2000
+intervals x 20 points (40 000 collocation nodes, L=360 008, m=240 000,
+nnz_J=12 479 754, nnz_H=12 799 740).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+* ``value``  device-resident throughput: inputs already in HBM, CUDA events on the
+  engine's stream around each step, L2 flushed (untimed) between steps.
+* ``e2e``    the same metric through the public API (System.objective / gradient /
+  constraints / jacobian / hessian) with HOST buffers: every step copies x (and
+  lambda, sigma) to the device and all five results back.
+* ``roofline`` the dominant kernel (pk_expand_blocks of the Hessian) against the
+  measured HBM copy bandwidth in MEASURED_PEAKS.json.
+* ``cpu_baseline`` / ``--impl reference``: the CPU oracle port (oracle/pockit_oracle.py,
+  a restatement of the reference's NumPy algorithm; the reference itself cannot
+  travel to the GPU box) timed on the host cores.
+
+N > 1 (torchrun): every rank evaluates its own independent OCP instance of the
+same shape (a parameter sweep sharded by instance, no data-path collective);
+``value`` = total eval-sets/s over all ranks, time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "NLP callback eval-sets/s (objective+gradient+constraints+Jacobian+Hessian) at 40k nodes"
+UNIT = "eval-sets/s"
+WORKLOAD = dict(builder="robot_arm", scheme="radau", mesh=2000, num_point=20)
+
+
+def workload_name():
+    return "robot_arm LGR 2000x20 (40000 nodes; BASELINE.json configs[1])"
+
+
+def build_system(seed_shift: int = 0):
+    import importlib
+
+    from pockit_b200 import problems
+
+    mod = importlib.import_module(f"pockit_b200.{WORKLOAD['scheme']}")
+    S = problems.BUILDERS[WORKLOAD["builder"]](mod, mesh=WORKLOAD["mesh"], num_point=WORKLOAD["num_point"])
+    x, lam, sigma = problems.evaluation_point(S, seed=1 + seed_shift)
+    return S, x, lam, sigma
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    seed_shift, sets = args
+    S, x, lam, sigma = build_system(seed_shift)
+    from oracle.pockit_oracle import OracleSystem
+
+    O = OracleSystem(S)
+
+    def one():
+        O.objective(x); O.gradient(x); O.constraints(x); O.jacobian(x); O.hessian(x, lam, sigma)
+
+    one()  # warm-up (lambdify caches, page faults)
+    t0 = time.perf_counter()
+    for _ in range(sets):
+        one()
+    return (time.perf_counter() - t0) / sets
+
+
+def cpu_eval_sets_per_s(workers: int, sets: int):
+    """Oracle port on `workers` host processes (the path itself is single-threaded)."""
+    if workers == 1:
+        per = [_cpu_worker((0, sets))]
+    else:
+        import multiprocessing as mp
+
+        with mp.get_context("spawn").Pool(workers) as pool:
+            per = pool.map(_cpu_worker, [(i, sets) for i in range(workers)])
+    return sum(1.0 / t for t in per), max(per)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = max(1, min(os.cpu_count() or 1, 8))
+    sets = max(1, args.steps)
+    value, worst = cpu_eval_sets_per_s(cores, sets)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * worst, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name()},
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sets} eval-set(s) per worker after 1 warm-up on {cores} independent worker processes "
+                      f"(oracle/pockit_oracle.py, NumPy restatement of the reference; one process is single-threaded)",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import __graft_entry__ as graft
+
+    graft.build()
+    from pockit_b200 import plan as P
+    from pockit_b200.engine import Engine
+
+    S, x, lam, sigma = build_system(seed_shift=rank)
+    lo = S.lowering
+    eng = Engine(lo, device=local)
+    S._engine = eng  # the public callbacks below run on this engine
+    S.pinned_outputs = True
+    eng.reuse_outputs = True
+    modes = [P.OBJ, P.GRAD, P.CONS, P.JAC, P.HESS]
+    for m in modes:
+        eng.load(m)
+    eng.upload(x, lam, sigma)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------
+    eng.time_steps(modes, max(3, args.warmup), flush_l2=True)
+    barrier()
+    launches0 = eng.launches
+    with ClockSampler(local) as clk:
+        ms = eng.time_steps(modes, args.steps, flush_l2=True)
+        eng.sync()
+    launches = eng.launches - launches0
+    barrier()
+    t_local = sum(ms) / 1000.0
+    if dist is not None:
+        t = torch.tensor([t_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_max = float(t.item())
+    else:
+        t_max = t_local
+    value = world * args.steps / t_max
+
+    # ---- end to end through the public API (host buffers in, host buffers out) -------------
+    def one_set():
+        S.objective(x); S.gradient(x); S.constraints(x); S.jacobian(x); S.hessian(x, lam, sigma)
+
+    for _ in range(max(3, args.warmup)):
+        one_set()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_set()
+    torch.cuda.synchronize()
+    e2e_local = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    else:
+        e2e_t = e2e_local
+    L, m, nj, nh = lo.r_s, lo.m, lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c
+    h2d = 8 * (5 * L + m + 1)
+    d2h = 8 * (1 + L + m + nj + nh)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    iters = 20
+    _, stages = eng.time(P.HESS, iters=iters, stages=True)
+    exp_ms = stages[P.ST_EXPAND] / iters
+    jobs = eng.fin[P.HESS]["jobs"][P.ST_EXPAND]
+    slots = int(sum(int(j["i"][1]) for j in jobs))
+    rows = len({int(j["i"][9]) for j in jobs})
+    n_mid = lo.phases[0].L_m
+    alg_bytes = 8 * (slots + rows * n_mid + lo.phases[0].col.n_rows * lo.phases[0].n_x)
+    achieved = alg_bytes / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else 0.0
+    set_bytes = 8 * (6 * L + 2 * m + nj + nh)
+    per_mode = {}
+    for mname, mm in zip(("objective", "gradient", "constraints", "jacobian", "hessian"), modes):
+        per_mode[mname] = eng.time(mm, iters=iters) / iters
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": workload_name(), "L": int(L), "m": int(m), "nnz_jac": int(nj), "nnz_hess": int(nh),
+            "l2": "flushed between steps (256 MiB fill, untimed)", "parallelism": f"{world} independent instance(s), one per GPU",
+            "set_algorithmic_MB": set_bytes / 1e6, "set_GBps": set_bytes / (t_max / args.steps) / 1e9,
+            "ms_per_callback": per_mode,
+        },
+        "roofline": {
+            "bound": "hbm", "kernel": "pk_expand_blocks (Hessian mode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": exp_ms,
+        },
+        "e2e": {"value": world * args.steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1000.0 * e2e_t / args.steps, "outputs": "page-locked engine buffers (System.pinned_outputs=True)"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, worst = cpu_eval_sets_per_s(1, 3)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "3 eval-sets of the same workload after 1 warm-up, oracle/pockit_oracle.py on one host core",
+        }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

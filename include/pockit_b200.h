@@ -142,6 +142,9 @@ int pk_download(pk_engine *e, int mode, double *out);
  * whole mode, ms_stage[s] the kernels of each stage (s = 0..PK_N_STAGES-1 jobs, PK_N_STAGES = node
  * programs, PK_N_STAGES+1 = system program), measured in separate passes. */
 int pk_time(pk_engine *e, int mode, int iters, float *ms_total, float *ms_stage /* [PK_N_STAGES+2] */);
+/* device-resident throughput: `steps` times { [flush L2, untimed]; event; run modes[0..n); event };
+ * ms_steps[s] is the CUDA-event time of step s on the engine stream */
+int pk_time_steps(pk_engine *e, const int *modes, int n_modes, int steps, int flush_l2, float *ms_steps);
 int pk_kernel_launches(pk_engine *e, int64_t *count); /* kernels launched so far by this engine */
 int pk_flush_l2(pk_engine *e);                        /* overwrite a buffer larger than L2 */
 

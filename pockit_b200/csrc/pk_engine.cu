@@ -38,6 +38,7 @@ struct ModeState {
   std::vector<pk_node_program> node_programs;
   cudaKernel_t sys_kernel = nullptr;
   long long n_scalar = 0, n_out = 0;
+  double* OUT = nullptr;  // [B][n_out], owned by the mode so that a full evaluation set stays resident
   std::vector<char> cubin;
   pk_job* jobs[PK_N_STAGES] = {};
   long long n_jobs[PK_N_STAGES] = {};
@@ -52,7 +53,7 @@ struct pk_engine {
   pk_dims dims;
   int device = 0;
   cudaStream_t stream = nullptr;
-  double *X = nullptr, *LAM = nullptr, *SIG = nullptr, *S = nullptr, *W = nullptr, *OUT = nullptr, *FIX = nullptr;
+  double *X = nullptr, *LAM = nullptr, *SIG = nullptr, *S = nullptr, *W = nullptr, *FIX = nullptr;
   double* dpool = nullptr; long long* ipool = nullptr;
   double *hX = nullptr, *hLAM = nullptr, *hSIG = nullptr, *hOUT = nullptr;  // pinned staging
   double* flush = nullptr; long long n_flush = 0;
@@ -103,7 +104,6 @@ extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   CK(dev(&e->SIG, B));
   CK(dev(&e->S, B * d->n_scalar));
   CK(dev(&e->W, d->n_table));
-  CK(dev(&e->OUT, B * n_out));
   CK(dev(&e->FIX, B * d->n_fixed));
   CK(cudaMemsetAsync(e->LAM, 0, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1), e->stream));
   CK(cudaMemsetAsync(e->SIG, 0, sizeof(double) * (size_t)B, e->stream));
@@ -127,6 +127,7 @@ static void free_mode(ModeState& ms) {
   if (ms.exp_job) cudaFree(ms.exp_job);
   if (ms.exp_chunk) cudaFree(ms.exp_chunk);
   if (ms.lib) cudaLibraryUnload(ms.lib);
+  if (ms.OUT) cudaFree(ms.OUT);
   ms = ModeState();
 }
 
@@ -135,7 +136,7 @@ extern "C" int pk_engine_destroy(pk_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (auto& ms : e->mode) free_mode(ms);
-  cudaFree(e->X); cudaFree(e->LAM); cudaFree(e->SIG); cudaFree(e->S); cudaFree(e->W); cudaFree(e->OUT);
+  cudaFree(e->X); cudaFree(e->LAM); cudaFree(e->SIG); cudaFree(e->S); cudaFree(e->W);
   cudaFree(e->FIX); cudaFree(e->dpool); cudaFree(e->ipool); cudaFree(e->flush);
   cudaFreeHost(e->hX); cudaFreeHost(e->hLAM); cudaFreeHost(e->hSIG); cudaFreeHost(e->hOUT);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -239,6 +240,7 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
   }
   ms.n_scalar = d->n_scalar;
   ms.n_out = d->n_out;
+  CK(cudaMalloc((void**)&ms.OUT, sizeof(double) * (size_t)e->dims.batch * (size_t)(d->n_out > 0 ? d->n_out : 1)));
   for (int s = 0; s < PK_N_STAGES; ++s) {
     ms.n_jobs[s] = d->n_jobs[s];
     if (d->n_jobs[s] > 0) {
@@ -277,7 +279,7 @@ extern "C" int pk_engine_get_cubin(pk_engine* e, int mode, const void** data, si
 
 static PkCtx make_ctx(pk_engine* e, const ModeState& ms) {
   PkCtx cx;
-  cx.X = e->X; cx.LAM = e->LAM; cx.SIG = e->SIG; cx.S = e->S; cx.W = e->W; cx.OUT = e->OUT;
+  cx.X = e->X; cx.LAM = e->LAM; cx.SIG = e->SIG; cx.S = e->S; cx.W = e->W; cx.OUT = ms.OUT;
   cx.dpool = e->dpool; cx.ipool = e->ipool;
   cx.L = e->dims.L; cx.m = e->dims.m; cx.n_scalar = ms.n_scalar; cx.n_out = ms.n_out;
   return cx;
@@ -299,7 +301,7 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
       const double* tm = e->dpool + np_.tm_offset;
       const double* wm = e->dpool + np_.wm_offset;
       int Bi = B;
-      void* args[] = {&e->X, &e->LAM, &e->FIX, &tm, &wm, &e->S, &e->W, &e->OUT, &Bi};
+      void* args[] = {&e->X, &e->LAM, &e->FIX, &tm, &wm, &e->S, &e->W, &ms.OUT, &Bi};
       const long long threads = (long long)B * np_.n_nodes;
       CK(cudaLaunchKernel((void*)ms.node_kernels[p], dim3(blocks_for(threads, 128)), dim3(128), args, 0, st));
       ++e->launches;
@@ -312,7 +314,7 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
   }
   if ((stage_mask & (1u << (PK_N_STAGES + 1))) && ms.sys_kernel) {
     int Bi = B;
-    void* args[] = {&e->X, &e->S, &e->OUT, &Bi};
+    void* args[] = {&e->X, &e->S, &ms.OUT, &Bi};
     CK(cudaLaunchKernel((void*)ms.sys_kernel, dim3(blocks_for(B, 64)), dim3(64), args, 0, st));
     ++e->launches;
   }
@@ -330,7 +332,7 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
     ++e->launches;
   }
   if (mode == PK_MODE_GRADIENT && (stage_mask & ((1u << PK_STAGE_GRAD_RANGE) | (1u << PK_STAGE_GRAD_SCALAR)))) {
-    CK(cudaMemsetAsync(e->OUT, 0, sizeof(double) * (size_t)B * (size_t)ms.n_out, st));
+    CK(cudaMemsetAsync(ms.OUT, 0, sizeof(double) * (size_t)B * (size_t)ms.n_out, st));
     if (ms.n_jobs[PK_STAGE_GRAD_RANGE]) {
       dim3 grid(blocks_for(ms.max_grad_count * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_GRAD_RANGE]);
       pk_grad_range<<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
@@ -388,7 +390,7 @@ extern "C" int pk_download(pk_engine* e, int mode, double* out) {
   CK(cudaSetDevice(e->device));
   const size_t n = sizeof(double) * (size_t)e->dims.batch * (size_t)e->mode[mode].n_out;
   // `out` may be pinned (pk_alloc_host) or pageable; the runtime handles both
-  CK(cudaMemcpyAsync(out, e->OUT, n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(out, e->mode[mode].OUT, n, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -433,6 +435,26 @@ extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float
       if (s == PK_STAGE_GRAD_SCALAR) { ms_stage[s] = 0.f; continue; }
       if (timed(mask, &ms_stage[s])) return 1;
     }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return 0;
+}
+
+extern "C" int pk_time_steps(pk_engine* e, const int* modes, int n_modes, int steps, int flush_l2, float* ms_steps) {
+  if (!e || !modes || n_modes < 1 || steps < 1 || !ms_steps) return fail("pk_time_steps: bad argument");
+  CK(cudaSetDevice(e->device));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  for (int s = 0; s < steps; ++s) {
+    if (flush_l2 && pk_flush_l2(e)) return 1;
+    CK(cudaEventRecord(a, e->stream));
+    for (int k = 0; k < n_modes; ++k)
+      if (launch_mode(e, modes[k], ~0u)) return 1;
+    CK(cudaEventRecord(b, e->stream));
+    CK(cudaEventSynchronize(b));
+    CK(cudaEventElapsedTime(&ms_steps[s], a, b));
+  }
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   return 0;

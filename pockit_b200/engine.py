@@ -86,6 +86,7 @@ def load_library():
         "pk_sync": ([vp], C.c_int),
         "pk_download": ([vp, C.c_int, vp], C.c_int),
         "pk_time": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
+        "pk_time_steps": ([vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "pk_kernel_launches": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "pk_flush_l2": ([vp], C.c_int),
         "pk_alloc_host": ([C.c_size_t], vp),
@@ -152,6 +153,8 @@ class Engine:
         self._check(self.lib.pk_engine_set_pools(h, _ptr(self._dpool), self._dpool.size, _ptr(self._ipool), self._ipool.size))
         self.set_fixed(fixed)
         self._loaded = set()
+        self._pinned = {}
+        self.reuse_outputs = False
         self._opts = ["--fmad=true"] if fastmath else []
         self._one = np.ones(self.B)
         self._zero_lam = np.zeros(self.B * max(1, lo.m))
@@ -223,6 +226,12 @@ class Engine:
     def _out(self, mode: int, out: Optional[np.ndarray]) -> np.ndarray:
         n = self.B * self.n_out[mode]
         if out is None:
+            if self.reuse_outputs:
+                # page-locked, engine-owned result buffers: D2H at full PCIe rate, no per-call
+                # allocation; the returned array is valid until the next call of the same callback
+                if mode not in self._pinned:
+                    self._pinned[mode] = PinnedArray(n)
+                return self._pinned[mode].array
             return np.empty(n, dtype=np.float64)
         if out.size != n or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise ValueError("out must be a contiguous float64 array of the callback's size")
@@ -304,6 +313,15 @@ class Engine:
         st = (C.c_float * (N_STAGES + 2))()
         self._check(self.lib.pk_time(self._h, mode, iters, C.byref(total), st if stages else None))
         return (total.value, list(st)) if stages else total.value
+
+    def time_steps(self, modes, steps: int, flush_l2: bool = True):
+        """Per-step CUDA-event times (ms) of running ``modes`` back to back, inputs resident in HBM."""
+        for m in modes:
+            self.load(m)
+        arr = (C.c_int * len(modes))(*modes)
+        out = (C.c_float * steps)()
+        self._check(self.lib.pk_time_steps(self._h, arr, len(modes), steps, int(flush_l2), out))
+        return list(out)
 
     def flush_l2(self):
         self._check(self.lib.pk_flush_l2(self._h))

@@ -93,6 +93,10 @@ class System:
         self._lowered: Optional["SystemLowering"] = None
         self._lowered_key = None
         self._engine = None
+        # False (default): every callback returns a fresh NumPy array like the reference.
+        # True: callbacks return views of engine-owned page-locked buffers (valid until the next
+        # call of the same callback) -- what a solver adapter that copies the values anyway wants.
+        self.pinned_outputs = False
         self.set_phase([])
         self.set_system_constraint([], [], [])
 
@@ -211,6 +215,7 @@ class System:
             if self._engine is not None:
                 self._engine.close()
             self._engine = Engine(self.lowering, fastmath=self._fastmath)
+        self._engine.reuse_outputs = self.pinned_outputs
         return self._engine
 
     def objective(self, x):
