@@ -46,7 +46,9 @@ struct ModeState {
   int* gen_job = nullptr; int* gen_chunk = nullptr; long long gen_blocks = 0;
   int* exp_job = nullptr; int* exp_chunk = nullptr; long long exp_blocks = 0;
   size_t exp_smem = 0;
-  long long max_defect_rows = 0, max_grad_count = 0;
+  long long max_defect_rows = 0, max_grad_count = 0, max_reduce_len = 0;
+  size_t def_smem = 0;
+  bool def_fast = false, def_table = false;
 };
 
 struct pk_engine {
@@ -195,10 +197,10 @@ static int compile(const pk_mode_desc* d, int device, std::vector<char>& cubin) 
   return 0;
 }
 
-static int build_block_map(const pk_job* jobs, long long n, int** d_job, int** d_chunk, long long* n_blocks) {
+static int build_block_map(const pk_job* jobs, long long n, int field, int per, int** d_job, int** d_chunk, long long* n_blocks) {
   std::vector<int> bj, bc;
   for (long long j = 0; j < n; ++j) {
-    const long long chunks = (jobs[j].i[1] + PK_CHUNK - 1) / PK_CHUNK;
+    const long long chunks = (jobs[j].i[field] + per - 1) / per;
     for (long long c = 0; c < chunks; ++c) {
       bj.push_back((int)j);
       bc.push_back((int)c);
@@ -248,8 +250,8 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
       CK(cudaMemcpy(ms.jobs[s], d->jobs[s], sizeof(pk_job) * (size_t)d->n_jobs[s], cudaMemcpyHostToDevice));
     }
   }
-  if (build_block_map(d->jobs[PK_STAGE_GENERIC], d->n_jobs[PK_STAGE_GENERIC], &ms.gen_job, &ms.gen_chunk, &ms.gen_blocks)) return 1;
-  if (build_block_map(d->jobs[PK_STAGE_EXPAND], d->n_jobs[PK_STAGE_EXPAND], &ms.exp_job, &ms.exp_chunk, &ms.exp_blocks)) return 1;
+  if (build_block_map(d->jobs[PK_STAGE_GENERIC], d->n_jobs[PK_STAGE_GENERIC], 1, PK_CHUNK, &ms.gen_job, &ms.gen_chunk, &ms.gen_blocks)) return 1;
+  if (build_block_map(d->jobs[PK_STAGE_EXPAND], d->n_jobs[PK_STAGE_EXPAND], 11, PK_THREADS, &ms.exp_job, &ms.exp_chunk, &ms.exp_blocks)) return 1;
   for (long long j = 0; j < d->n_jobs[PK_STAGE_EXPAND]; ++j) {
     const pk_job& jb = d->jobs[PK_STAGE_EXPAND][j];
     const size_t sm = sizeof(double) * (size_t)(jb.i[3] * jb.i[4]);
@@ -261,8 +263,24 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     CK(cudaFuncSetAttribute(pk_expand_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.exp_smem));
   }
   for (long long j = 0; j < d->n_jobs[PK_STAGE_DEFECT]; ++j) {
-    const long long r = d->jobs[PK_STAGE_DEFECT][j].i[4] * d->jobs[PK_STAGE_DEFECT][j].i[3];
+    const pk_job& jb = d->jobs[PK_STAGE_DEFECT][j];
+    const long long r = jb.i[4] * jb.i[3];
     if (r > ms.max_defect_rows) ms.max_defect_rows = r;
+    if (jb.i[13]) {
+      const size_t sm = sizeof(double) * (size_t)(jb.flags * (jb.i[13] | 1));
+      if (sm > ms.def_smem) ms.def_smem = sm;
+      ms.def_fast = true;
+    } else {
+      ms.def_table = true;
+    }
+  }
+  if (ms.def_smem > 48 * 1024) {
+    if (ms.def_smem > 200 * 1024) return fail("integration block too large for shared memory");
+    CK(cudaFuncSetAttribute(pk_defects_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.def_smem));
+  }
+  for (long long j = 0; j < d->n_jobs[PK_STAGE_REDUCE]; ++j) {
+    const long long len = d->jobs[PK_STAGE_REDUCE][j].i[3] - d->jobs[PK_STAGE_REDUCE][j].i[2];
+    if (len > ms.max_reduce_len) ms.max_reduce_len = len;
   }
   for (long long j = 0; j < d->n_jobs[PK_STAGE_GRAD_RANGE]; ++j)
     if (d->jobs[PK_STAGE_GRAD_RANGE][j].i[1] > ms.max_grad_count) ms.max_grad_count = d->jobs[PK_STAGE_GRAD_RANGE][j].i[1];
@@ -309,7 +327,10 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
   }
   if ((stage_mask & (1u << PK_STAGE_REDUCE)) && ms.n_jobs[PK_STAGE_REDUCE]) {
     const long long warps = ms.n_jobs[PK_STAGE_REDUCE] * (long long)B;
-    pk_reduce_rows<<<blocks_for(warps * 32, PK_THREADS), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B);
+    if (ms.max_reduce_len >= 2048)
+      pk_reduce_rows_block<<<(unsigned)warps, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B);
+    else
+      pk_reduce_rows<<<blocks_for(warps * 32, PK_THREADS), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B);
     ++e->launches;
   }
   if ((stage_mask & (1u << (PK_N_STAGES + 1))) && ms.sys_kernel) {
@@ -320,8 +341,14 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
   }
   if ((stage_mask & (1u << PK_STAGE_DEFECT)) && ms.n_jobs[PK_STAGE_DEFECT]) {
     dim3 grid(blocks_for(ms.max_defect_rows * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_DEFECT]);
-    pk_defects<<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
-    ++e->launches;
+    if (ms.def_table) {
+      pk_defects<<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+      ++e->launches;
+    }
+    if (ms.def_fast) {
+      pk_defects_blocks<<<grid, PK_THREADS, ms.def_smem, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+      ++e->launches;
+    }
   }
   if ((stage_mask & (1u << PK_STAGE_GENERIC)) && ms.gen_blocks) {
     pk_generic_jobs<<<dim3((unsigned)ms.gen_blocks, B), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk);

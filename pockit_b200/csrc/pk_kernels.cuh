@@ -23,7 +23,8 @@
 //   DEFECT   i0 x offset of the phase, i1 L_x, i2 L_m, i3 n_x, i4 rows per state,
 //            i5 ipool row_ptr, i6 ipool cols, i7 dpool data (full operator, row-major),
 //            i8 ipool +1 column per row, i9 ipool -1 column per row, i10 W base of f_0 (rows consecutive),
-//            i11 scalar header (dt, front values, back values), i12 first output row
+//            i11 scalar header (dt, front values, back values), i12 first output row,
+//            i13 n | 0, flags rows per block, i14 dpool unit block, i15 dpool widths (same-order fast path)
 //   GENERIC  i0 dst, i1 count, i2 lam row offset (-1: none), i3 system scalar slot (-1: none),
 //            i4 post factor (0 none, 1 sigma, 2 lam[i5]), f0 sign
 //     CONST         i6 dpool values
@@ -33,7 +34,8 @@
 //     SYS           -
 //     OUTER / TRIL  A: i6 i7 i8, B: i9 i10 i11 (as SCALED; F_*_SCALAR / F_*_UNIT), i12 length of B
 //   EXPAND   i0 dst, i1 count, i2 lam row of the first block row (-1), i3 n (block columns), i4 block rows,
-//            i5 node step per interval, i6 first node, i7 dpool unit block, i8 dpool widths, i9 W base, i10 L_m, f0 sign
+//            i5 node step per interval, i6 first node, i7 dpool unit block, i8 dpool widths, i9 W base, i10 L_m,
+//            i11 (interval, column) pairs = intervals * n, f0 sign
 //   GRAD_RANGE   i0 dst, i1 count, i2 ipool contributions (W base, L_m, c_lo, system slot) x i3
 //   GRAD_SCALAR  i0 dst, i2 ipool contributions (scalar slot | -1, system slot) x i3
 #pragma once
@@ -64,7 +66,8 @@ struct PkCtx {
 };
 
 // ---------------------------------------------------------------------------------------------
-// one warp per (job, instance): fixed-order strided accumulation + shuffle tree (deterministic)
+// row sums, deterministic (fixed strides + fixed tree).  Short rows (batched small problems): one
+// warp per (job, instance); long rows (fine meshes): one block per (job, instance).
 __global__ void __launch_bounds__(PK_THREADS) pk_reduce_rows(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
   const int warp = (blockIdx.x * PK_THREADS + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -79,11 +82,41 @@ __global__ void __launch_bounds__(PK_THREADS) pk_reduce_rows(PkCtx cx, const pk_
   if (lane == 0) cx.S[(long long)b * cx.n_scalar + jb.i[4]] = acc;
 }
 
+__global__ void __launch_bounds__(PK_THREADS) pk_reduce_rows_block(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
+  __shared__ double part[PK_THREADS / 32];
+  const int j = blockIdx.x % n_jobs, b = blockIdx.x / n_jobs;
+  const pk_job& jb = jobs[j];
+  const double* row = cx.W + jb.i[0] + (long long)b * jb.i[1];
+  const long long lo = jb.i[2], hi = jb.i[3];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent chains keep loads in flight
+  long long c = lo + threadIdx.x;
+  for (; c + 3 * PK_THREADS < hi; c += 4 * PK_THREADS) {
+    a0 += row[c];
+    a1 += row[c + PK_THREADS];
+    a2 += row[c + 2 * PK_THREADS];
+    a3 += row[c + 3 * PK_THREADS];
+  }
+  for (; c < hi; c += PK_THREADS) a0 += row[c];
+  double acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < PK_THREADS / 32; ++w) t += part[w];
+    cx.S[(long long)b * cx.n_scalar + jb.i[4]] = t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // one thread per defect row; the I.f sum runs over the row's entries in column order, dt is
-// applied after the sum, exactly like `T_v.dot(x) - I_m.dot(f) * dt`
+// applied after the sum, exactly like `T_v.dot(x) - I_m.dot(f) * dt`.  Table-driven version for
+// meshes with mixed orders (or blocks that lost exact zeros):
 __global__ void __launch_bounds__(PK_THREADS) pk_defects(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
   const pk_job& jb = jobs[blockIdx.y];
+  if (jb.i[13]) return;  // handled by pk_defects_blocks
   const long long rows = jb.i[4], n_x = jb.i[3];
   const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
   if (gid >= rows * n_x * B) return;
@@ -110,11 +143,53 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects(PkCtx cx, const pk_job*
   cx.OUT[(long long)b * cx.n_out + jb.i[12] + (long long)i * rows + r] = tx - acc * Sb[0];
 }
 
+// Same-order meshes: the operator is never read from memory.  i13 = n (points per interval),
+// flags = rows per block (= node step = offset of the -1 column: n-1 for LGL, n for LGR),
+// i14 dpool unit block (rows x n), i15 dpool interval widths.  Entries are (unit * width) / 2.
+__global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
+  extern __shared__ double unit_s[];
+  const pk_job& jb = jobs[blockIdx.y];
+  const int n = (int)jb.i[13];
+  if (!n) return;
+  const int rb = jb.flags;
+  const int ld = n | 1;  // odd row stride: conflict-free when consecutive lanes walk consecutive rows
+  const double* unit = cx.dpool + jb.i[14];
+  for (int t = threadIdx.x; t < rb * n; t += PK_THREADS) unit_s[(t / n) * ld + (t % n)] = unit[t];
+  __syncthreads();
+  const long long rows = jb.i[4], n_x = jb.i[3];
+  const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
+  if (gid >= rows * n_x * B) return;
+  const int b = (int)(gid / (rows * n_x));
+  const long long rem = gid - (long long)b * rows * n_x;
+  const int i = (int)(rem / rows);
+  const long long r = rem - (long long)i * rows;
+  const long long K = r / rb;
+  const int rr = (int)(r - K * rb);
+  const long long Lx = jb.i[1], Lm = jb.i[2];
+  const double* Sb = cx.S + (long long)b * cx.n_scalar + jb.i[11];
+  const double* xv = cx.X + (long long)b * cx.L + jb.i[0] + (long long)i * Lx;
+  const double* f = cx.W + jb.i[10] + ((long long)i * B + b) * Lm + K * rb;
+  const double w = cx.dpool[jb.i[15] + K];
+  const double* u = unit_s + rr * ld;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int c = 0; c < n; ++c) acc += ((u[c] * w) / 2.0) * f[c];
+  const long long cp = K * rb + rr, cn = K * rb + rb;
+  const double xp = cp == 0 ? Sb[1 + i] : (cp == Lx - 1 ? Sb[1 + n_x + i] : xv[cp]);
+  const double xn = cn == 0 ? Sb[1 + i] : (cn == Lx - 1 ? Sb[1 + n_x + i] : xv[cn]);
+  double tx = 0.0;
+  tx += 1.0 * xp;
+  tx += -1.0 * xn;
+  cx.OUT[(long long)b * cx.n_out + jb.i[12] + (long long)i * rows + r] = tx - acc * Sb[0];
+}
+
 // ---------------------------------------------------------------------------------------------
 // block-structured expansion: every interior interval contributes a dense (rows x n) block whose
 // entries are (unit[r][c] * width_K) / 2 -- the reference's `I_lgl(n) * d / 2` -- so the operator
-// never has to be read from memory: the unit block sits in shared memory and slot -> (K, r, c) is
-// pure arithmetic.  A job never exceeds 2^32 slots (the planner splits longer runs).
+// never has to be read from memory: the (sign-folded) unit block sits in shared memory.
+// One thread owns one (interval, column) pair = one node of one list: it loads the node's list
+// value once and walks down the block column, so consecutive lanes write consecutive slots of a
+// block row (runs of n doubles) with ~8 instructions per 8-byte store.  i11 = pairs = intervals * n.
 __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const pk_job* __restrict__ jobs,
                                                               const int* __restrict__ blk_job,
                                                               const int* __restrict__ blk_chunk) {
@@ -124,29 +199,24 @@ __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const p
   const int n = (int)jb.i[3], rows = (int)jb.i[4];
   const int bn = n * rows;
   const double* unit = cx.dpool + jb.i[7];
-  for (int t = threadIdx.x; t < bn; t += PK_THREADS) unit_s[t] = unit[t];
-  __syncthreads();
-  const double* width = cx.dpool + jb.i[8];
-  const double* src = cx.W + jb.i[9] + (long long)b * jb.i[10];
-  const double* lam = cx.LAM + (long long)b * cx.m + jb.i[2];
-  double* out = cx.OUT + (long long)b * cx.n_out + jb.i[0];
-  const bool use_lam = jb.flags & PK_F_LAM;
   const double sign = jb.f[0];
-  const long long count = jb.i[1];
-  const unsigned e0 = (unsigned)blk_chunk[blockIdx.x] * PK_CHUNK + threadIdx.x;
-  const int step = (int)jb.i[5];
-  const long long c0 = jb.i[6];
-#pragma unroll
-  for (int it = 0; it < PK_ITEMS; ++it) {
-    const unsigned e = e0 + it * PK_THREADS;  // consecutive threads -> consecutive slots
-    if (e >= count) break;
-    const unsigned K = e / (unsigned)bn;
-    const unsigned rem = e - K * (unsigned)bn;
-    const unsigned r = rem / (unsigned)n;
-    const unsigned cc = rem - r * (unsigned)n;
-    double v = sign * ((unit_s[rem] * width[K]) / 2.0);
-    if (use_lam) v = v * lam[K * rows + r];
-    out[e] = v * src[c0 + (long long)K * step + cc];
+  for (int t = threadIdx.x; t < bn; t += PK_THREADS) unit_s[t] = sign * unit[t];  // exact: sign is +-1
+  __syncthreads();
+  const unsigned t = (unsigned)blk_chunk[blockIdx.x] * PK_THREADS + threadIdx.x;
+  if (t >= (unsigned)jb.i[11]) return;
+  const unsigned K = t / (unsigned)n;
+  const unsigned cc = t - K * (unsigned)n;
+  const double w = cx.dpool[jb.i[8] + K];
+  const double s = cx.W[jb.i[9] + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc];
+  double* out = cx.OUT + (long long)b * cx.n_out + jb.i[0] + (long long)K * bn + cc;
+  const double* u = unit_s + cc;
+  if (jb.flags & PK_F_LAM) {
+    const double* lam = cx.LAM + (long long)b * cx.m + jb.i[2] + (long long)K * rows;
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) out[r * n] = (((u[r * n] * w) / 2.0) * lam[r]) * s;
+  } else {
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) out[r * n] = ((u[r * n] * w) / 2.0) * s;
   }
 }
 

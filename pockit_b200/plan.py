@@ -262,9 +262,10 @@ class ModePlan:
             if p.n_x:
                 d = own.defect_tables[pi]
                 self.job(
-                    ST_DEFECT, i0=lo.l_p[pi], i1=col.L_x, i2=col.L_m, i3=p.n_x, i4=col.n_rows,
+                    ST_DEFECT, 0, d["rows_blk"], i0=lo.l_p[pi], i1=col.L_x, i2=col.L_m, i3=p.n_x, i4=col.n_rows,
                     i5=d["row_ptr"], i6=d["col"], i7=d["data"], i8=d["tpos"], i9=d["tneg"],
                     i10=("row", fd_rows[0]), i11=own.header[pi], i12=base,
+                    i13=d["n"], i14=d["unit"], i15=d["width"],
                 )
             pbase = base + col.n_rows * p.n_x
             for q in range(p.n_c):
@@ -408,6 +409,7 @@ class ModePlan:
                         i0=dst + piece["k0"], i1=piece["count"], i2=(lam + piece["row0"]) if has_lam else -1,
                         i3=piece["n"], i4=piece["rows"], i5=piece["step"], i6=piece["c0"],
                         i7=piece["unit"], i8=piece["width"], i9=("row", row), i10=col.L_m,
+                        i11=piece["count"] // piece["rows"],
                     )
         else:  # direct
             lam = sg.lam_base + seg.lam_off if has_lam else -1
@@ -471,7 +473,16 @@ class DevicePlan:
         tpos[trow[tval > 0]] = tcol[tval > 0]
         tneg[trow[tval < 0]] = tcol[tval < 0]
         P = self.pools
-        return dict(row_ptr=P.int(row_ptr), col=P.int(cols), data=P.dbl(data), tpos=P.int(tpos), tneg=P.int(tneg))
+        fast = dict(n=0, rows_blk=0, unit=0, width=0)
+        if col.same_order and col.dense_blocks:
+            from .discretization import _unit_integration_block
+
+            n = int(col.num_point[0])
+            unit = _unit_integration_block(col.scheme, n)
+            fast = dict(n=n, rows_blk=unit.shape[0], unit=P.dbl(unit.ravel()), width=P.dbl(col.width))
+        return dict(
+            row_ptr=P.int(row_ptr), col=P.int(cols), data=P.dbl(data), tpos=P.int(tpos), tneg=P.int(tneg), **fast
+        )
 
     def _expand_pieces(self, p):
         """Split the middle part of the integration operator into runs the EXPAND
