@@ -63,50 +63,60 @@ def build_system(seed_shift: int = 0):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML (same counters nvidia-smi prints)
+    every ~2 ms from a thread while the timed regions run."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.h = None
+        try:
+            import pynvml
+
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
-            )
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __exit__(self, *exc):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop.set()
+        if self.h is not None:
+            self.thread.join(timeout=1)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        seen = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.rows))
+        return {"sm_mhz": statistics.median(sm for sm, _ in self.rows), "sm_max_mhz": self.max_sm,
+                "reasons": seen, "samples": len(self.rows)}
 
 
 # --------------------------------------------------------------------------- CPU arm
@@ -143,7 +153,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = max(1, min(os.cpu_count() or 1, 8))
-    sets = max(1, args.steps)
+    sets = max(1, min(args.steps, 5))  # bounded sample: ~1 s per set and worker
     value, worst = cpu_eval_sets_per_s(cores, sets)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -164,7 +174,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -214,9 +224,10 @@ def main():
     eng.time_steps(modes, max(3, args.warmup), flush_l2=True)
     barrier()
     launches0 = eng.launches
-    with ClockSampler(local) as clk:
-        ms = eng.time_steps(modes, args.steps, flush_l2=True)
-        eng.sync()
+    clk = ClockSampler(local)
+    clk.__enter__()
+    ms = eng.time_steps(modes, args.steps, flush_l2=True)
+    eng.sync()
     launches = eng.launches - launches0
     barrier()
     t_local = sum(ms) / 1000.0
@@ -240,12 +251,21 @@ def main():
         one_set()
     torch.cuda.synchronize()
     e2e_local = time.perf_counter() - t0
+    clk.__exit__()
     if dist is not None:
         t = torch.tensor([e2e_local], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t = float(t.item())
     else:
         e2e_t = e2e_local
+    e2e_each = {}
+    for cname, fn in (("objective", lambda: S.objective(x)), ("gradient", lambda: S.gradient(x)),
+                      ("constraints", lambda: S.constraints(x)), ("jacobian", lambda: S.jacobian(x)),
+                      ("hessian", lambda: S.hessian(x, lam, sigma))):
+        t0 = time.perf_counter()
+        for _ in range(5):
+            fn()
+        e2e_each[cname] = 1000.0 * (time.perf_counter() - t0) / 5
     L, m, nj, nh = lo.r_s, lo.m, lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c
     h2d = 8 * (5 * L + m + 1)
     d2h = 8 * (1 + L + m + nj + nh)
@@ -290,7 +310,7 @@ def main():
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": exp_ms,
         },
         "e2e": {"value": world * args.steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1000.0 * e2e_t / args.steps, "outputs": "page-locked engine buffers (System.pinned_outputs=True)"},
+                "ms_per_step": 1000.0 * e2e_t / args.steps, "ms_per_callback": e2e_each, "outputs": "page-locked engine buffers (System.pinned_outputs=True)"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }

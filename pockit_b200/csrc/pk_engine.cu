@@ -48,6 +48,7 @@ struct ModeState {
   size_t exp_smem = 0;
   long long max_defect_rows = 0, max_grad_count = 0, max_reduce_len = 0;
   size_t def_smem = 0;
+  double* red_partial = nullptr; unsigned* red_ticket = nullptr; int red_parts = 0;
   bool def_fast = false, def_table = false;
 };
 
@@ -130,6 +131,8 @@ static void free_mode(ModeState& ms) {
   if (ms.exp_chunk) cudaFree(ms.exp_chunk);
   if (ms.lib) cudaLibraryUnload(ms.lib);
   if (ms.OUT) cudaFree(ms.OUT);
+  if (ms.red_partial) cudaFree(ms.red_partial);
+  if (ms.red_ticket) cudaFree(ms.red_ticket);
   ms = ModeState();
 }
 
@@ -282,6 +285,13 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     const long long len = d->jobs[PK_STAGE_REDUCE][j].i[3] - d->jobs[PK_STAGE_REDUCE][j].i[2];
     if (len > ms.max_reduce_len) ms.max_reduce_len = len;
   }
+  if (ms.max_reduce_len >= 2048) {
+    ms.red_parts = (int)((ms.max_reduce_len + PK_REDUCE_SPAN - 1) / PK_REDUCE_SPAN);
+    const size_t n = (size_t)d->n_jobs[PK_STAGE_REDUCE] * (size_t)e->dims.batch;
+    CK(cudaMalloc((void**)&ms.red_partial, sizeof(double) * n * (size_t)ms.red_parts));
+    CK(cudaMalloc((void**)&ms.red_ticket, sizeof(unsigned) * n));
+    CK(cudaMemset(ms.red_ticket, 0, sizeof(unsigned) * n));
+  }
   for (long long j = 0; j < d->n_jobs[PK_STAGE_GRAD_RANGE]; ++j)
     if (d->jobs[PK_STAGE_GRAD_RANGE][j].i[1] > ms.max_grad_count) ms.max_grad_count = d->jobs[PK_STAGE_GRAD_RANGE][j].i[1];
   ms.loaded = true;
@@ -327,8 +337,9 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
   }
   if ((stage_mask & (1u << PK_STAGE_REDUCE)) && ms.n_jobs[PK_STAGE_REDUCE]) {
     const long long warps = ms.n_jobs[PK_STAGE_REDUCE] * (long long)B;
-    if (ms.max_reduce_len >= 2048)
-      pk_reduce_rows_block<<<(unsigned)warps, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B);
+    if (ms.red_parts)
+      pk_reduce_rows_block<<<(unsigned)(warps * ms.red_parts), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B,
+                                                                                   ms.red_parts, ms.red_partial, ms.red_ticket);
     else
       pk_reduce_rows<<<blocks_for(warps * 32, PK_THREADS), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B);
     ++e->launches;

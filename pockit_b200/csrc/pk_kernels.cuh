@@ -82,31 +82,53 @@ __global__ void __launch_bounds__(PK_THREADS) pk_reduce_rows(PkCtx cx, const pk_
   if (lane == 0) cx.S[(long long)b * cx.n_scalar + jb.i[4]] = acc;
 }
 
-__global__ void __launch_bounds__(PK_THREADS) pk_reduce_rows_block(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
-  __shared__ double part[PK_THREADS / 32];
-  const int j = blockIdx.x % n_jobs, b = blockIdx.x / n_jobs;
+// Long rows: PK_REDUCE_SPAN elements per block -> partial sums; the block that takes the last
+// ticket of its (job, instance) adds the partials in index order, so the result does not depend
+// on scheduling.  `partial` holds [job][instance][part], `ticket` one self-resetting counter each.
+#define PK_REDUCE_SPAN 1024
+__global__ void __launch_bounds__(PK_THREADS) pk_reduce_rows_block(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B,
+                                                                  int parts, double* __restrict__ partial,
+                                                                  unsigned* __restrict__ ticket) {
+  __shared__ double warp_sum[PK_THREADS / 32];
+  __shared__ bool is_last;
+  const int part = blockIdx.x % parts;
+  const int jbi = blockIdx.x / parts;  // = b * n_jobs + j
+  const int j = jbi % n_jobs, b = jbi / n_jobs;
   const pk_job& jb = jobs[j];
   const double* row = cx.W + jb.i[0] + (long long)b * jb.i[1];
-  const long long lo = jb.i[2], hi = jb.i[3];
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four independent chains keep loads in flight
-  long long c = lo + threadIdx.x;
-  for (; c + 3 * PK_THREADS < hi; c += 4 * PK_THREADS) {
-    a0 += row[c];
-    a1 += row[c + PK_THREADS];
-    a2 += row[c + 2 * PK_THREADS];
-    a3 += row[c + 3 * PK_THREADS];
+  const long long lo = jb.i[2] + (long long)part * PK_REDUCE_SPAN;
+  const long long hi = jb.i[3] < lo + PK_REDUCE_SPAN ? (long long)jb.i[3] : lo + PK_REDUCE_SPAN;
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < PK_REDUCE_SPAN / PK_THREADS; ++k) {
+    const long long c = lo + threadIdx.x + k * PK_THREADS;
+    if (c < hi) acc += row[c];
   }
-  for (; c < hi; c += PK_THREADS) a0 += row[c];
-  double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < PK_THREADS / 32; ++w) t += part[w];
-    cx.S[(long long)b * cx.n_scalar + jb.i[4]] = t;
+    for (int w = 0; w < PK_THREADS / 32; ++w) t += warp_sum[w];
+    partial[(long long)jbi * parts + part] = t;
+    __threadfence();
+    is_last = atomicAdd(&ticket[jbi], 1u) == (unsigned)(parts - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 32) {
+    const int used = (int)((jb.i[3] - jb.i[2] + PK_REDUCE_SPAN - 1) / PK_REDUCE_SPAN);
+    double t = 0.0;
+    for (int q = threadIdx.x; q < used; q += 32) t += ((volatile double*)partial)[(long long)jbi * parts + q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) {
+      cx.S[(long long)b * cx.n_scalar + jb.i[4]] = t;
+      ticket[jbi] = 0u;
+    }
   }
 }
 

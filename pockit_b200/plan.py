@@ -235,6 +235,14 @@ class ModePlan:
         program stores ``g_k(c) * w_c`` in a table row, a REDUCE job sums it."""
         lo = self.owner.lo
         self.int_sum_slot = {}
+        # only integrals that a needed system-level expression really reads
+        used = set()
+        for lf in self.sys_need:
+            fn = lo.F_o if lf.key[0] == "o" else lo.F_c[lf.key[1]]
+            e = fn.expr if lf.kind == "sF" else (fn.G_expr if lf.kind == "sG" else fn.H_expr)[lf.key[-1]]
+            used |= e.free_symbols
+        for pi, p in enumerate(lo.phases):
+            self.int_needed[pi] &= np.array([sym in used for sym in p.I], dtype=bool)
         for pi, p in enumerate(lo.phases):
             for k in range(p.n_I):
                 if self.int_needed[pi][k]:
