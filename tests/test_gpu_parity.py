@@ -57,3 +57,70 @@ def test_callbacks_match_oracle(builder, scheme, kw):
     assert_close(S.constraints(x), O.constraints(x), "constraints")
     assert_close(S.jacobian(x), O.jacobian(x), "jacobian")
     assert_close(S.hessian(x, lam, 0.7), O.hessian(x, lam, 0.7), "hessian")
+
+
+def test_batched_instances_match_per_instance_oracle():
+    """BASELINE configs[4] in small: quadrotor LGL 14x6, instances differing only in the
+    FIXED initial state; every instance must match an oracle built for that instance."""
+    import pockit_b200.lobatto as lob
+    from oracle.pockit_oracle import OracleSystem
+    from pockit_b200 import problems
+    from pockit_b200.batched import BatchedSystem, fixed_index, fixed_table
+
+    B = 6
+    rng = np.random.default_rng(0)
+    starts = rng.uniform(-0.2, 0.2, size=(B, 2))
+    S = problems.quadrotor(lob, fastmath=False)
+    fixed = fixed_table(S, B)
+    fixed[:, fixed_index(S, 0, "x0", 0)] = starts[:, 0]
+    fixed[:, fixed_index(S, 0, "x0", 1)] = starts[:, 1]
+    x0, lam0, _ = problems.evaluation_point(S)
+    X = x0[None, :] + 1e-2 * rng.normal(size=(B, len(x0)))
+    LAM = lam0[None, :] + 0.1 * rng.normal(size=(B, len(lam0)))
+    sig = rng.uniform(0.5, 1.5, B)
+    bs = BatchedSystem(S, fixed)
+    obj, grad, cons = bs.objective(X), bs.gradient(X), bs.constraints(X)
+    jac, hess = bs.jacobian(X), bs.hessian(X, LAM, sig)
+    assert jac.shape == (B, len(S.jacobianstructure()[0]))
+    for b in range(B):
+        O = OracleSystem(problems.quadrotor(lob, start=tuple(starts[b]), fastmath=False))
+        assert_close(obj[b], O.objective(X[b]), f"objective[{b}]")
+        assert_close(grad[b], O.gradient(X[b]), f"gradient[{b}]")
+        assert_close(cons[b], O.constraints(X[b]), f"constraints[{b}]")
+        assert_close(jac[b], O.jacobian(X[b]), f"jacobian[{b}]")
+        assert_close(hess[b], O.hessian(X[b], LAM[b], sig[b]), f"hessian[{b}]")
+    bs.close()
+
+
+def test_size_independent_properties_at_full_size():
+    """BASELINE configs[1] at full size (40 000 nodes): properties that need no oracle run.
+    Hessian values are linear in (lambda, sigma); the Jacobian is the derivative of the
+    constraints (directional finite difference); callbacks are idempotent and leave x alone."""
+    import pockit_b200.radau as rad
+    from pockit_b200 import problems
+
+    S = problems.robot_arm(rad, 2000, 20)
+    x, lam, _ = problems.evaluation_point(S)
+    assert S.L == 360008 and len(S.c_lb) == 240000
+    jr, jc = S.jacobianstructure()
+    hr, hc = S.hessianstructure()
+    assert len(jr) == 12479754 and len(hr) == 12799740
+    assert np.all(hr >= hc)  # lower triangle
+    x_in = x.copy()
+    j1, j2 = S.jacobian(x), S.jacobian(x)
+    assert np.array_equal(j1, j2) and np.array_equal(x, x_in)
+    rng = np.random.default_rng(3)
+    lam2 = rng.normal(size=len(lam))
+    h_a = S.hessian(x, lam, 1.0)
+    h_b = S.hessian(x, lam2, 0.0)
+    h_ab = S.hessian(x, 2.0 * lam + lam2, 2.0)
+    np.testing.assert_allclose(h_ab, 2.0 * h_a + h_b, rtol=1e-10, atol=1e-10)
+    d = rng.normal(size=S.L)
+    eps = 1e-6
+    fd = (S.constraints(x + eps * d) - S.constraints(x - eps * d)) / (2 * eps)
+    jd = np.zeros(len(lam))
+    np.add.at(jd, jr, j1 * d[jc])
+    np.testing.assert_allclose(jd, fd, rtol=1e-5, atol=1e-6)
+    g = S.gradient(x)
+    fdo = (S.objective(x + eps * d) - S.objective(x - eps * d)) / (2 * eps)
+    np.testing.assert_allclose(g @ d, fdo, rtol=1e-6, atol=1e-8)
