@@ -285,8 +285,8 @@ def main():
     _, stages = eng.time(P.HESS, iters=iters, stages=True)
     exp_ms = stages[P.ST_EXPAND] / iters
     jobs = eng.fin[P.HESS]["jobs"][P.ST_EXPAND]
-    slots = int(sum(int(j["i"][1]) for j in jobs))
-    rows = len({int(j["i"][9]) for j in jobs})
+    slots = int(sum(int(j["i"][1]) * int(j["i"][11]) * int(j["i"][4]) for j in jobs))  # lists x pairs x block rows
+    rows = int(sum(int(j["i"][1]) for j in jobs))
     n_mid = lo.phases[0].L_m
     alg_bytes = 8 * (slots + rows * n_mid + lo.phases[0].col.n_rows * lo.phases[0].n_x)
     achieved = alg_bytes / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else 0.0

@@ -136,13 +136,17 @@ int pk_eval_hessian(pk_engine *e, const double *x, const double *lambda /* [B][m
 int pk_upload_x(pk_engine *e, const double *x);
 int pk_upload_multipliers(pk_engine *e, const double *lambda, const double *sigma);
 int pk_run(pk_engine *e, int mode);               /* enqueue the mode's kernels on the engine stream */
+/* enqueue several callbacks at the same x as one CUDA graph: each mode on its own stream (private
+ * tables and outputs), forked from / joined to the engine stream -- the "evaluate the whole set at
+ * this x" entry point an x-keyed cache in the solver adapter calls */
+int pk_run_set(pk_engine *e, const int *modes, int n_modes);
 int pk_sync(pk_engine *e);
 int pk_download(pk_engine *e, int mode, double *out);
 /* time `iters` back-to-back runs with CUDA events on the engine stream; ms_total covers the
  * whole mode, ms_stage[s] the kernels of each stage (s = 0..PK_N_STAGES-1 jobs, PK_N_STAGES = node
  * programs, PK_N_STAGES+1 = system program), measured in separate passes. */
 int pk_time(pk_engine *e, int mode, int iters, float *ms_total, float *ms_stage /* [PK_N_STAGES+2] */);
-/* device-resident throughput: `steps` times { [flush L2, untimed]; event; run modes[0..n); event };
+/* device-resident throughput: `steps` times { [flush L2, untimed]; event; pk_run_set(modes); event };
  * ms_steps[s] is the CUDA-event time of step s on the engine stream */
 int pk_time_steps(pk_engine *e, const int *modes, int n_modes, int steps, int flush_l2, float *ms_steps);
 int pk_kernel_launches(pk_engine *e, int64_t *count); /* kernels launched so far by this engine */

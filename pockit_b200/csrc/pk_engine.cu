@@ -39,6 +39,9 @@ struct ModeState {
   cudaKernel_t sys_kernel = nullptr;
   long long n_scalar = 0, n_out = 0;
   double* OUT = nullptr;  // [B][n_out], owned by the mode so that a full evaluation set stays resident
+  double *S = nullptr, *W = nullptr;  // scalar / node tables of this mode (modes may run concurrently)
+  cudaStream_t stream = nullptr;      // used when a whole evaluation set is launched at once
+  cudaEvent_t done = nullptr;
   std::vector<char> cubin;
   pk_job* jobs[PK_N_STAGES] = {};
   long long n_jobs[PK_N_STAGES] = {};
@@ -56,13 +59,16 @@ struct pk_engine {
   pk_dims dims;
   int device = 0;
   cudaStream_t stream = nullptr;
-  double *X = nullptr, *LAM = nullptr, *SIG = nullptr, *S = nullptr, *W = nullptr, *FIX = nullptr;
+  double *X = nullptr, *LAM = nullptr, *SIG = nullptr, *FIX = nullptr;
+  cudaEvent_t fork = nullptr;
+  cudaGraphExec_t set_graph = nullptr;  // captured evaluation set (all requested modes, one stream each)
+  std::vector<int> set_modes;
   double* dpool = nullptr; long long* ipool = nullptr;
   double *hX = nullptr, *hLAM = nullptr, *hSIG = nullptr, *hOUT = nullptr;  // pinned staging
   double* flush = nullptr; long long n_flush = 0;
   long long n_out_max = 0;
   ModeState mode[PK_N_MODES];
-  long long launches = 0;
+  long long launches = 0, set_launches = 0;
 };
 
 extern "C" int pk_abi_version(void) { return PK_ABI_VERSION; }
@@ -105,12 +111,10 @@ extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   CK(dev(&e->X, B * d->L));
   CK(dev(&e->LAM, B * d->m));
   CK(dev(&e->SIG, B));
-  CK(dev(&e->S, B * d->n_scalar));
-  CK(dev(&e->W, d->n_table));
   CK(dev(&e->FIX, B * d->n_fixed));
   CK(cudaMemsetAsync(e->LAM, 0, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1), e->stream));
   CK(cudaMemsetAsync(e->SIG, 0, sizeof(double) * (size_t)B, e->stream));
-  CK(cudaMemsetAsync(e->S, 0, sizeof(double) * (size_t)(B * d->n_scalar > 0 ? B * d->n_scalar : 1), e->stream));
+  CK(cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&e->hX, sizeof(double) * (size_t)(B * d->L > 0 ? B * d->L : 1)));
   CK(cudaMallocHost((void**)&e->hLAM, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1)));
   CK(cudaMallocHost((void**)&e->hSIG, sizeof(double) * (size_t)B));
@@ -131,6 +135,10 @@ static void free_mode(ModeState& ms) {
   if (ms.exp_chunk) cudaFree(ms.exp_chunk);
   if (ms.lib) cudaLibraryUnload(ms.lib);
   if (ms.OUT) cudaFree(ms.OUT);
+  if (ms.S) cudaFree(ms.S);
+  if (ms.W) cudaFree(ms.W);
+  if (ms.stream) cudaStreamDestroy(ms.stream);
+  if (ms.done) cudaEventDestroy(ms.done);
   if (ms.red_partial) cudaFree(ms.red_partial);
   if (ms.red_ticket) cudaFree(ms.red_ticket);
   ms = ModeState();
@@ -141,7 +149,9 @@ extern "C" int pk_engine_destroy(pk_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (auto& ms : e->mode) free_mode(ms);
-  cudaFree(e->X); cudaFree(e->LAM); cudaFree(e->SIG); cudaFree(e->S); cudaFree(e->W);
+  cudaFree(e->X); cudaFree(e->LAM); cudaFree(e->SIG);
+  if (e->set_graph) cudaGraphExecDestroy(e->set_graph);
+  if (e->fork) cudaEventDestroy(e->fork);
   cudaFree(e->FIX); cudaFree(e->dpool); cudaFree(e->ipool); cudaFree(e->flush);
   cudaFreeHost(e->hX); cudaFreeHost(e->hLAM); cudaFreeHost(e->hSIG); cudaFreeHost(e->hOUT);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -246,6 +256,20 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
   ms.n_scalar = d->n_scalar;
   ms.n_out = d->n_out;
   CK(cudaMalloc((void**)&ms.OUT, sizeof(double) * (size_t)e->dims.batch * (size_t)(d->n_out > 0 ? d->n_out : 1)));
+  {
+    const size_t ns = sizeof(double) * (size_t)e->dims.batch * (size_t)(d->n_scalar > 0 ? d->n_scalar : 1);
+    const size_t nw = sizeof(double) * (size_t)(e->dims.n_table > 0 ? e->dims.n_table : 1);
+    CK(cudaMalloc((void**)&ms.S, ns));
+    CK(cudaMalloc((void**)&ms.W, nw));
+    CK(cudaMemset(ms.S, 0, ns));
+    CK(cudaStreamCreateWithFlags(&ms.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
+  }
+  if (e->set_graph) {  // a re-loaded mode invalidates the captured set
+    cudaGraphExecDestroy(e->set_graph);
+    e->set_graph = nullptr;
+    e->set_modes.clear();
+  }
   for (int s = 0; s < PK_N_STAGES; ++s) {
     ms.n_jobs[s] = d->n_jobs[s];
     if (d->n_jobs[s] > 0) {
@@ -259,7 +283,7 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     const pk_job& jb = d->jobs[PK_STAGE_EXPAND][j];
     const size_t sm = sizeof(double) * (size_t)(jb.i[3] * jb.i[4]);
     if (sm > ms.exp_smem) ms.exp_smem = sm;
-    if (jb.i[1] >= (1LL << 32)) return fail("expand job longer than 2^32 slots");
+    if (jb.i[11] >= (1LL << 31)) return fail("expand job with more than 2^31 (interval, column) pairs");
   }
   if (ms.exp_smem > 48 * 1024) {
     if (ms.exp_smem > 200 * 1024) return fail("integration block too large for shared memory");
@@ -307,7 +331,7 @@ extern "C" int pk_engine_get_cubin(pk_engine* e, int mode, const void** data, si
 
 static PkCtx make_ctx(pk_engine* e, const ModeState& ms) {
   PkCtx cx;
-  cx.X = e->X; cx.LAM = e->LAM; cx.SIG = e->SIG; cx.S = e->S; cx.W = e->W; cx.OUT = ms.OUT;
+  cx.X = e->X; cx.LAM = e->LAM; cx.SIG = e->SIG; cx.S = ms.S; cx.W = ms.W; cx.OUT = ms.OUT;
   cx.dpool = e->dpool; cx.ipool = e->ipool;
   cx.L = e->dims.L; cx.m = e->dims.m; cx.n_scalar = ms.n_scalar; cx.n_out = ms.n_out;
   return cx;
@@ -317,19 +341,18 @@ static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n +
 
 // stage_mask selects which parts run (bit s = job stage s, bit PK_N_STAGES = node programs,
 // bit PK_N_STAGES + 1 = system program); used by pk_time to attribute time.
-static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
+static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t st) {
   ModeState& ms = e->mode[mode];
   if (!ms.loaded) return fail("mode not loaded");
   const int B = e->dims.batch;
   PkCtx cx = make_ctx(e, ms);
-  cudaStream_t st = e->stream;
   if (stage_mask & (1u << PK_N_STAGES)) {
     for (size_t p = 0; p < ms.node_kernels.size(); ++p) {
       const pk_node_program& np_ = ms.node_programs[p];
       const double* tm = e->dpool + np_.tm_offset;
       const double* wm = e->dpool + np_.wm_offset;
       int Bi = B;
-      void* args[] = {&e->X, &e->LAM, &e->FIX, &tm, &wm, &e->S, &e->W, &ms.OUT, &Bi};
+      void* args[] = {&e->X, &e->LAM, &e->FIX, &tm, &wm, &ms.S, &ms.W, &ms.OUT, &Bi};
       const long long threads = (long long)B * np_.n_nodes;
       CK(cudaLaunchKernel((void*)ms.node_kernels[p], dim3(blocks_for(threads, 128)), dim3(128), args, 0, st));
       ++e->launches;
@@ -346,7 +369,7 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask) {
   }
   if ((stage_mask & (1u << (PK_N_STAGES + 1))) && ms.sys_kernel) {
     int Bi = B;
-    void* args[] = {&e->X, &e->S, &ms.OUT, &Bi};
+    void* args[] = {&e->X, &ms.S, &ms.OUT, &Bi};
     CK(cudaLaunchKernel((void*)ms.sys_kernel, dim3(blocks_for(B, 64)), dim3(64), args, 0, st));
     ++e->launches;
   }
@@ -414,7 +437,7 @@ extern "C" int pk_upload_multipliers(pk_engine* e, const double* lambda, const d
 extern "C" int pk_run(pk_engine* e, int mode) {
   if (!e || mode < 0 || mode >= PK_N_MODES) return fail("pk_run: bad argument");
   CK(cudaSetDevice(e->device));
-  return launch_mode(e, mode, ~0u);
+  return launch_mode(e, mode, ~0u, e->stream);
 }
 
 extern "C" int pk_sync(pk_engine* e) {
@@ -436,7 +459,7 @@ extern "C" int pk_download(pk_engine* e, int mode, double* out) {
 static int eval(pk_engine* e, int mode, const double* x, const double* lam, const double* sig, double* out) {
   if (pk_upload_x(e, x)) return 1;
   if (mode == PK_MODE_HESSIAN && pk_upload_multipliers(e, lam, sig)) return 1;
-  if (launch_mode(e, mode, ~0u)) return 1;
+  if (launch_mode(e, mode, ~0u, e->stream)) return 1;
   return pk_download(e, mode, out);
 }
 
@@ -459,7 +482,7 @@ extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventRecord(a, e->stream));
     for (int i = 0; i < iters; ++i)
-      if (launch_mode(e, mode, mask)) return 1;
+      if (launch_mode(e, mode, mask, e->stream)) return 1;
     CK(cudaEventRecord(b, e->stream));
     CK(cudaEventSynchronize(b));
     CK(cudaEventElapsedTime(out, a, b));
@@ -478,6 +501,50 @@ extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float
   return 0;
 }
 
+// Launch several callbacks at the same x as ONE graph: every mode runs on its own stream (its
+// tables and output buffer are private), forked from and joined to the engine stream, so the
+// latency-bound small callbacks overlap the HBM-bound expansions and the host pays one launch.
+static int run_set(pk_engine* e, const int* modes, int n_modes) {
+  std::vector<int> want(modes, modes + n_modes);
+  if (!e->set_graph || want != e->set_modes) {
+    for (int k = 0; k < n_modes; ++k)
+      if (modes[k] < 0 || modes[k] >= PK_N_MODES || !e->mode[modes[k]].loaded) return fail("pk_run_set: mode not loaded");
+    if (e->set_graph) cudaGraphExecDestroy(e->set_graph);
+    e->set_graph = nullptr;
+    cudaGraph_t graph = nullptr;
+    const long long before = e->launches;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    CK(cudaEventRecord(e->fork, e->stream));
+    int rc = 0;
+    for (int k = 0; k < n_modes && !rc; ++k) {
+      ModeState& ms = e->mode[modes[k]];
+      if (cudaStreamWaitEvent(ms.stream, e->fork, 0) != cudaSuccess) rc = 1;
+      if (!rc) rc = launch_mode(e, modes[k], ~0u, ms.stream);
+      if (!rc && cudaEventRecord(ms.done, ms.stream) != cudaSuccess) rc = 1;
+      if (!rc && cudaStreamWaitEvent(e->stream, ms.done, 0) != cudaSuccess) rc = 1;
+    }
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc ? 1 : fail("pk_run_set: stream capture failed");
+    }
+    e->set_launches = e->launches - before;
+    e->launches = before;
+    CK(cudaGraphInstantiate(&e->set_graph, graph, 0));
+    cudaGraphDestroy(graph);
+    e->set_modes = want;
+  }
+  CK(cudaGraphLaunch(e->set_graph, e->stream));
+  e->launches += e->set_launches;
+  return 0;
+}
+
+extern "C" int pk_run_set(pk_engine* e, const int* modes, int n_modes) {
+  if (!e || !modes || n_modes < 1) return fail("pk_run_set: bad argument");
+  CK(cudaSetDevice(e->device));
+  return run_set(e, modes, n_modes);
+}
+
 extern "C" int pk_time_steps(pk_engine* e, const int* modes, int n_modes, int steps, int flush_l2, float* ms_steps) {
   if (!e || !modes || n_modes < 1 || steps < 1 || !ms_steps) return fail("pk_time_steps: bad argument");
   CK(cudaSetDevice(e->device));
@@ -487,8 +554,7 @@ extern "C" int pk_time_steps(pk_engine* e, const int* modes, int n_modes, int st
   for (int s = 0; s < steps; ++s) {
     if (flush_l2 && pk_flush_l2(e)) return 1;
     CK(cudaEventRecord(a, e->stream));
-    for (int k = 0; k < n_modes; ++k)
-      if (launch_mode(e, modes[k], ~0u)) return 1;
+    if (run_set(e, modes, n_modes)) return 1;
     CK(cudaEventRecord(b, e->stream));
     CK(cudaEventSynchronize(b));
     CK(cudaEventElapsedTime(&ms_steps[s], a, b));

@@ -33,7 +33,8 @@
 //     SCALED        i6 W base | scalar slot (F_A_SCALAR), i7 L_m, i8 c_lo
 //     SYS           -
 //     OUTER / TRIL  A: i6 i7 i8, B: i9 i10 i11 (as SCALED; F_*_SCALAR / F_*_UNIT), i12 length of B
-//   EXPAND   i0 dst, i1 count, i2 lam row of the first block row (-1), i3 n (block columns), i4 block rows,
+//   EXPAND   i0 ipool list table (dst, W row base) x i1 lists, i2 lam row of the first block row (-1),
+//            i3 n (block columns), i4 block rows,
 //            i5 node step per interval, i6 first node, i7 dpool unit block, i8 dpool widths, i9 W base, i10 L_m,
 //            i11 (interval, column) pairs = intervals * n, f0 sign
 //   GRAD_RANGE   i0 dst, i1 count, i2 ipool contributions (W base, L_m, c_lo, system slot) x i3
@@ -209,9 +210,11 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const 
 // block-structured expansion: every interior interval contributes a dense (rows x n) block whose
 // entries are (unit[r][c] * width_K) / 2 -- the reference's `I_lgl(n) * d / 2` -- so the operator
 // never has to be read from memory: the (sign-folded) unit block sits in shared memory.
-// One thread owns one (interval, column) pair = one node of one list: it loads the node's list
-// value once and walks down the block column, so consecutive lanes write consecutive slots of a
-// block row (runs of n doubles) with ~8 instructions per 8-byte store.  i11 = pairs = intervals * n.
+// A job covers ALL lists of one state (they share the block geometry and the multiplier rows).
+// One thread owns one (interval, column) pair = one node: it builds 8 entries of its coefficient
+// column, (unit*w)/2 [* lam_r], in registers and streams them against every list's value at that
+// node -- ~3 instructions per 8-byte store; consecutive lanes write runs of n consecutive slots.
+#define PK_ROW_TILE 8
 __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const pk_job* __restrict__ jobs,
                                                               const int* __restrict__ blk_job,
                                                               const int* __restrict__ blk_chunk) {
@@ -229,16 +232,32 @@ __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const p
   const unsigned K = t / (unsigned)n;
   const unsigned cc = t - K * (unsigned)n;
   const double w = cx.dpool[jb.i[8] + K];
-  const double s = cx.W[jb.i[9] + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc];
-  double* out = cx.OUT + (long long)b * cx.n_out + jb.i[0] + (long long)K * bn + cc;
+  const long long* __restrict__ lists = cx.ipool + jb.i[0];  // (dst, W row base) per list
+  const int nl = (int)jb.i[1];
+  const double* __restrict__ src = cx.W + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc;
+  double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + (long long)K * bn + cc;
   const double* u = unit_s + cc;
-  if (jb.flags & PK_F_LAM) {
-    const double* lam = cx.LAM + (long long)b * cx.m + jb.i[2] + (long long)K * rows;
-#pragma unroll 4
-    for (int r = 0; r < rows; ++r) out[r * n] = (((u[r * n] * w) / 2.0) * lam[r]) * s;
-  } else {
-#pragma unroll 4
-    for (int r = 0; r < rows; ++r) out[r * n] = ((u[r * n] * w) / 2.0) * s;
+  const bool use_lam = jb.flags & PK_F_LAM;
+  const double* lam = cx.LAM + (long long)b * cx.m + jb.i[2] + (long long)K * rows;
+  for (int r0 = 0; r0 < rows; r0 += PK_ROW_TILE) {
+    double a[PK_ROW_TILE];
+#pragma unroll
+    for (int j = 0; j < PK_ROW_TILE; ++j) {
+      const int r = r0 + j;
+      double v = 0.0;
+      if (r < rows) {
+        v = (u[r * n] * w) / 2.0;
+        if (use_lam) v = v * lam[r];
+      }
+      a[j] = v;
+    }
+    for (int l = 0; l < nl; ++l) {
+      const double sv = src[lists[2 * l + 1]];
+      double* o = out + lists[2 * l] + (long long)r0 * n;
+#pragma unroll
+      for (int j = 0; j < PK_ROW_TILE; ++j)
+        if (r0 + j < rows) o[j * n] = a[j] * sv;
+    }
   }
 }
 

@@ -83,6 +83,7 @@ def load_library():
         "pk_upload_x": ([vp, vp], C.c_int),
         "pk_upload_multipliers": ([vp, vp, vp], C.c_int),
         "pk_run": ([vp, C.c_int], C.c_int),
+        "pk_run_set": ([vp, C.POINTER(C.c_int), C.c_int], C.c_int),
         "pk_sync": ([vp], C.c_int),
         "pk_download": ([vp, C.c_int, vp], C.c_int),
         "pk_time": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
@@ -297,6 +298,13 @@ class Engine:
     def run(self, mode: int):
         self.load(mode)
         self._check(self.lib.pk_run(self._h, mode))
+
+    def run_set(self, modes):
+        """Enqueue several callbacks at the uploaded x as one graph (modes overlap)."""
+        for m in modes:
+            self.load(m)
+        arr = (C.c_int * len(modes))(*modes)
+        self._check(self.lib.pk_run_set(self._h, arr, len(modes)))
 
     def sync(self):
         self._check(self.lib.pk_sync(self._h))

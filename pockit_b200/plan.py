@@ -125,6 +125,7 @@ class ModePlan:
         self.int_needed = [np.zeros(p.n_I, dtype=bool) for p in lo.phases]
         self.n_out = 0
         self.src = None
+        self.expand_groups: dict = {}
         self._build()
 
     # ---------------------------------------------------------------- allocation helpers
@@ -412,13 +413,20 @@ class ModePlan:
                         i6=piece["row"], i7=piece["col"], i8=piece["data"], i9=("row", row), i10=col.L_m,
                     )
                 else:
-                    self.job(
-                        ST_EXPAND, 0, F_LAM if has_lam else 0, f0=seg.sign,
-                        i0=dst + piece["k0"], i1=piece["count"], i2=(lam + piece["row0"]) if has_lam else -1,
-                        i3=piece["n"], i4=piece["rows"], i5=piece["step"], i6=piece["c0"],
-                        i7=piece["unit"], i8=piece["width"], i9=("row", row), i10=col.L_m,
-                        i11=piece["count"] // piece["rows"],
-                    )
+                    # all lists of one state share geometry and multiplier rows: one job, a list table
+                    key = (pi, lam, seg.sign, piece["k0"])
+                    rec = self.expand_groups.get(key)
+                    if rec is None:
+                        rec = self.job(
+                            ST_EXPAND, 0, F_LAM if has_lam else 0, f0=seg.sign,
+                            i2=(lam + piece["row0"]) if has_lam else -1,
+                            i3=piece["n"], i4=piece["rows"], i5=piece["step"], i6=piece["c0"],
+                            i7=piece["unit"], i8=piece["width"], i10=col.L_m,
+                            i11=piece["count"] // piece["rows"],
+                        )
+                        rec["lists"] = []
+                        self.expand_groups[key] = rec
+                    rec["lists"].append((dst + piece["k0"], row))
         else:  # direct
             lam = sg.lam_base + seg.lam_off if has_lam else -1
             t = seg.terms[0]
@@ -570,6 +578,10 @@ class DevicePlan:
                     for cn, row in rows.items():
                         flat[4 * cn] = mp.row_base(row)
                     iv[2] = self.pools.int(flat)
+                if "lists" in rec:
+                    flat = [v for dst_, row in rec["lists"] for v in (dst_, mp.row_base(row))]
+                    iv[0] = self.pools.int(flat)
+                    iv[1] = len(rec["lists"])
                 arr[n] = (rec["type"], rec["flags"], iv, rec["f"])
             jobs[stage] = arr
         return dict(

@@ -214,14 +214,16 @@ class HostEmu:
         sign = jb["f"][0]
         n, rows, step, c0 = i[3], i[4], i[5], i[6]
         bn = n * rows
-        e = np.arange(i[1])
+        nK = i[11] // n
+        e = np.arange(nK * bn)
         K, rem = e // bn, e % bn
         r, cc = rem // n, rem % n
         unit = self.dpool[i[7] : i[7] + bn]
-        nK = int(K.max()) + 1
         width = self.dpool[i[8] : i[8] + nK]
+        lists = self.ipool[i[0] : i[0] + 2 * i[1]].reshape(-1, 2)
         for b in range(self.B):
             v = sign * ((unit[rem] * width[K]) / 2.0)
             if fl & P.F_LAM:
                 v = v * LAM[b, i[2] + K * rows + r]
-            OUT[b, i[0] : i[0] + i[1]] = v * W[i[9] + b * i[10] + c0 + K * step + cc]
+            for dst, wbase in lists:
+                OUT[b, dst : dst + len(e)] = v * W[wbase + b * i[10] + c0 + K * step + cc]

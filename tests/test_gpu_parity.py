@@ -124,3 +124,26 @@ def test_size_independent_properties_at_full_size():
     g = S.gradient(x)
     fdo = (S.objective(x + eps * d) - S.objective(x - eps * d)) / (2 * eps)
     np.testing.assert_allclose(g @ d, fdo, rtol=1e-6, atol=1e-8)
+
+
+def test_evaluation_set_graph_matches_single_callbacks():
+    """pk_run_set (all callbacks at one x as one graph, one stream per mode) must give
+    exactly what the five separate host-to-host callbacks give."""
+    import pockit_b200.lobatto as lob
+    from pockit_b200 import plan as P
+    from pockit_b200 import problems
+
+    S = problems.rocket(lob, mesh=30, num_point=8)
+    x, lam, sigma = problems.evaluation_point(S, seed=5)
+    single = {
+        P.OBJ: np.atleast_1d(S.objective(x)), P.GRAD: S.gradient(x), P.CONS: S.constraints(x),
+        P.JAC: S.jacobian(x), P.HESS: S.hessian(x, lam, sigma),
+    }
+    eng = S.engine
+    modes = [P.OBJ, P.GRAD, P.CONS, P.JAC, P.HESS]
+    eng.upload(x, lam, sigma)
+    for _ in range(3):  # replays of the captured graph
+        eng.run_set(modes)
+    eng.sync()
+    for m in modes:
+        assert np.array_equal(np.atleast_1d(eng.download(m)), single[m]), P.MODES[m]
