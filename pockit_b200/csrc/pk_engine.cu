@@ -213,7 +213,8 @@ static int compile(const pk_mode_desc* d, int device, std::vector<char>& cubin) 
 static int build_block_map(const pk_job* jobs, long long n, int field, int per, int** d_job, int** d_chunk, long long* n_blocks) {
   std::vector<int> bj, bc;
   for (long long j = 0; j < n; ++j) {
-    const long long chunks = (jobs[j].i[field] + per - 1) / per;
+    long long chunks = (jobs[j].i[field] + per - 1) / per;
+    if (field == 11) chunks *= (jobs[j].i[1] + PK_LIST_CHUNK - 1) / PK_LIST_CHUNK;  // expand: x list chunks
     for (long long c = 0; c < chunks; ++c) {
       bj.push_back((int)j);
       bc.push_back((int)c);

@@ -211,10 +211,12 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const 
 // entries are (unit[r][c] * width_K) / 2 -- the reference's `I_lgl(n) * d / 2` -- so the operator
 // never has to be read from memory: the (sign-folded) unit block sits in shared memory.
 // A job covers ALL lists of one state (they share the block geometry and the multiplier rows).
-// One thread owns one (interval, column) pair = one node: it builds 8 entries of its coefficient
-// column, (unit*w)/2 [* lam_r], in registers and streams them against every list's value at that
-// node -- ~3 instructions per 8-byte store; consecutive lanes write runs of n consecutive slots.
-#define PK_ROW_TILE 8
+// One thread owns one (interval, column) pair = one node and PK_LIST_CHUNK lists: it loads the
+// node's list values first (independent loads), then builds PK_ROW_TILE entries of its coefficient
+// column, (unit*w)/2 [* lam_r], at a time and streams them against the list values; consecutive
+// lanes write runs of n consecutive slots.
+#define PK_ROW_TILE 4
+#define PK_LIST_CHUNK 2
 __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const pk_job* __restrict__ jobs,
                                                               const int* __restrict__ blk_job,
                                                               const int* __restrict__ blk_chunk) {
@@ -227,15 +229,29 @@ __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const p
   const double sign = jb.f[0];
   for (int t = threadIdx.x; t < bn; t += PK_THREADS) unit_s[t] = sign * unit[t];  // exact: sign is +-1
   __syncthreads();
-  const unsigned t = (unsigned)blk_chunk[blockIdx.x] * PK_THREADS + threadIdx.x;
-  if (t >= (unsigned)jb.i[11]) return;
+  // chunk = list_chunk * pair_chunks + pair_chunk
+  const unsigned pairs = (unsigned)jb.i[11];
+  const unsigned pair_chunks = (pairs + PK_THREADS - 1) / PK_THREADS;
+  const unsigned chunk = (unsigned)blk_chunk[blockIdx.x];
+  const unsigned lc = chunk / pair_chunks;
+  const unsigned t = (chunk - lc * pair_chunks) * PK_THREADS + threadIdx.x;
+  if (t >= pairs) return;
   const unsigned K = t / (unsigned)n;
   const unsigned cc = t - K * (unsigned)n;
-  const double w = cx.dpool[jb.i[8] + K];
-  const long long* __restrict__ lists = cx.ipool + jb.i[0];  // (dst, W row base) per list
-  const int nl = (int)jb.i[1];
+  const long long* __restrict__ lists = cx.ipool + jb.i[0] + 2 * (long long)lc * PK_LIST_CHUNK;  // (dst, W row base)
+  const int nl = min((int)jb.i[1] - (int)lc * PK_LIST_CHUNK, PK_LIST_CHUNK);
   const double* __restrict__ src = cx.W + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc;
   double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + (long long)K * bn + cc;
+  // the node's value in every list of this chunk: independent loads, issued before any store
+  double sv[PK_LIST_CHUNK];
+  long long dst[PK_LIST_CHUNK];
+#pragma unroll
+  for (int l = 0; l < PK_LIST_CHUNK; ++l) {
+    const int ll = l < nl ? l : 0;
+    dst[l] = lists[2 * ll];
+    sv[l] = src[lists[2 * ll + 1]];
+  }
+  const double w = cx.dpool[jb.i[8] + K];
   const double* u = unit_s + cc;
   const bool use_lam = jb.flags & PK_F_LAM;
   const double* lam = cx.LAM + (long long)b * cx.m + jb.i[2] + (long long)K * rows;
@@ -251,12 +267,14 @@ __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const p
       }
       a[j] = v;
     }
-    for (int l = 0; l < nl; ++l) {
-      const double sv = src[lists[2 * l + 1]];
-      double* o = out + lists[2 * l] + (long long)r0 * n;
 #pragma unroll
-      for (int j = 0; j < PK_ROW_TILE; ++j)
-        if (r0 + j < rows) o[j * n] = a[j] * sv;
+    for (int l = 0; l < PK_LIST_CHUNK; ++l) {
+      if (l < nl) {
+        double* o = out + dst[l] + (long long)r0 * n;
+#pragma unroll
+        for (int j = 0; j < PK_ROW_TILE; ++j)
+          if (r0 + j < rows) o[j * n] = a[j] * sv[l];
+      }
     }
   }
 }
