@@ -285,7 +285,7 @@ def main():
     _, stages = eng.time(P.HESS, iters=iters, stages=True)
     exp_ms = stages[P.ST_EXPAND] / iters
     jobs = eng.fin[P.HESS]["jobs"][P.ST_EXPAND]
-    slots = int(sum(int(j["i"][1]) * int(j["i"][11]) * int(j["i"][3]) * int(j["i"][4]) for j in jobs))  # lists x intervals x block
+    slots = int(sum(int(j["i"][1]) * int(j["i"][11]) * int(j["i"][4]) for j in jobs))  # lists x pairs x block rows
     rows = int(sum(int(j["i"][1]) for j in jobs))
     n_mid = lo.phases[0].L_m
     alg_bytes = 8 * (slots + rows * n_mid + lo.phases[0].col.n_rows * lo.phases[0].n_x)

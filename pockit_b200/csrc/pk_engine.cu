@@ -214,10 +214,7 @@ static int build_block_map(const pk_job* jobs, long long n, int field, int per, 
   std::vector<int> bj, bc;
   for (long long j = 0; j < n; ++j) {
     long long chunks = (jobs[j].i[field] + per - 1) / per;
-    if (field == 11) {  // expand: interval groups x list chunks
-      const long long G = PK_THREADS / jobs[j].i[3];
-      chunks = ((jobs[j].i[11] + G - 1) / G) * ((jobs[j].i[1] + PK_LIST_CHUNK - 1) / PK_LIST_CHUNK);
-    }
+    if (field == 11) chunks *= (jobs[j].i[1] + PK_LIST_CHUNK - 1) / PK_LIST_CHUNK;  // expand: x list chunks
     for (long long c = 0; c < chunks; ++c) {
       bj.push_back((int)j);
       bc.push_back((int)c);
@@ -285,10 +282,9 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
   if (build_block_map(d->jobs[PK_STAGE_EXPAND], d->n_jobs[PK_STAGE_EXPAND], 11, PK_THREADS, &ms.exp_job, &ms.exp_chunk, &ms.exp_blocks)) return 1;
   for (long long j = 0; j < d->n_jobs[PK_STAGE_EXPAND]; ++j) {
     const pk_job& jb = d->jobs[PK_STAGE_EXPAND][j];
-    if (jb.i[3] > PK_THREADS) return fail("expand job: more than 256 points per interval (planner should use the table path)");
-    const long long bn = jb.i[3] * jb.i[4];
-    const size_t sm = sizeof(double) * (size_t)(((bn + 1) & ~1LL) + (PK_THREADS / jb.i[3]) * bn);
+    const size_t sm = sizeof(double) * (size_t)(jb.i[3] * jb.i[4]);
     if (sm > ms.exp_smem) ms.exp_smem = sm;
+    if (jb.i[11] >= (1LL << 31)) return fail("expand job with more than 2^31 (interval, column) pairs");
   }
   if (ms.exp_smem > 48 * 1024) {
     if (ms.exp_smem > 200 * 1024) return fail("integration block too large for shared memory");

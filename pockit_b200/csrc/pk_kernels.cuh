@@ -36,7 +36,7 @@
 //   EXPAND   i0 ipool list table (dst, W row base) x i1 lists, i2 lam row of the first block row (-1),
 //            i3 n (block columns), i4 block rows,
 //            i5 node step per interval, i6 first node, i7 dpool unit block, i8 dpool widths, i9 W base, i10 L_m,
-//            i11 intervals, f0 sign
+//            i11 (interval, column) pairs = intervals * n, f0 sign
 //   GRAD_RANGE   i0 dst, i1 count, i2 ipool contributions (W base, L_m, c_lo, system slot) x i3
 //   GRAD_SCALAR  i0 dst, i2 ipool contributions (scalar slot | -1, system slot) x i3
 #pragma once
@@ -211,75 +211,71 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const 
 // entries are (unit[r][c] * width_K) / 2 -- the reference's `I_lgl(n) * d / 2` -- so the operator
 // never has to be read from memory: the (sign-folded) unit block sits in shared memory.
 // A job covers ALL lists of one state (they share the block geometry and the multiplier rows).
-// A CTA owns G = 256 / n whole intervals and PK_LIST_CHUNK lists.  Thread (interval, column)
-// loads its node's list values (independent loads, before any store), then per list fills the
-// CTA's contiguous G x rows x n output tile in shared memory; the whole CTA then streams the tile
-// to HBM with aligned 16-byte stores, consecutive lanes -> consecutive addresses.  The slot
-// order of the reference makes that tile one contiguous run of the output.
-// i11 = number of intervals of the job.
+// One thread owns one (interval, column) pair = one node and PK_LIST_CHUNK lists: it loads the
+// node's list values first (independent loads), then builds PK_ROW_TILE entries of its coefficient
+// column, (unit*w)/2 [* lam_r], at a time and streams them against the list values; consecutive
+// lanes write runs of n consecutive slots.
+#define PK_ROW_TILE 4
 #define PK_LIST_CHUNK 2
 __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const pk_job* __restrict__ jobs,
                                                               const int* __restrict__ blk_job,
                                                               const int* __restrict__ blk_chunk) {
-  extern __shared__ double smem[];
+  extern __shared__ double unit_s[];
   const pk_job& jb = jobs[blk_job[blockIdx.x]];
   const int b = blockIdx.y;
   const int n = (int)jb.i[3], rows = (int)jb.i[4];
   const int bn = n * rows;
-  double* unit_s = smem;
-  double* tile = smem + ((bn + 1) & ~1);  // keep the tile 16-byte aligned
   const double* unit = cx.dpool + jb.i[7];
   const double sign = jb.f[0];
   for (int t = threadIdx.x; t < bn; t += PK_THREADS) unit_s[t] = sign * unit[t];  // exact: sign is +-1
-  const int G = PK_THREADS / n;
-  const int nK = (int)jb.i[11];
-  const int k_chunks = (nK + G - 1) / G;
-  const int chunk = blk_chunk[blockIdx.x];  // = list_chunk * k_chunks + interval_chunk
-  const int lc = chunk / k_chunks;
-  const int K0 = (chunk - lc * k_chunks) * G;
-  const int nKb = min(G, nK - K0);
-  const int Kl = threadIdx.x / n;
-  const int cc = threadIdx.x - Kl * n;
-  const bool active = Kl < nKb;
-  const int K = K0 + Kl;
+  __syncthreads();
+  // chunk = list_chunk * pair_chunks + pair_chunk
+  const unsigned pairs = (unsigned)jb.i[11];
+  const unsigned pair_chunks = (pairs + PK_THREADS - 1) / PK_THREADS;
+  const unsigned chunk = (unsigned)blk_chunk[blockIdx.x];
+  const unsigned lc = chunk / pair_chunks;
+  const unsigned t = (chunk - lc * pair_chunks) * PK_THREADS + threadIdx.x;
+  if (t >= pairs) return;
+  const unsigned K = t / (unsigned)n;
+  const unsigned cc = t - K * (unsigned)n;
   const long long* __restrict__ lists = cx.ipool + jb.i[0] + 2 * (long long)lc * PK_LIST_CHUNK;  // (dst, W row base)
-  const int nl = min((int)jb.i[1] - lc * PK_LIST_CHUNK, PK_LIST_CHUNK);
+  const int nl = min((int)jb.i[1] - (int)lc * PK_LIST_CHUNK, PK_LIST_CHUNK);
+  const double* __restrict__ src = cx.W + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc;
+  double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + (long long)K * bn + cc;
+  // the node's value in every list of this chunk: independent loads, issued before any store
   double sv[PK_LIST_CHUNK];
-  double w = 0.0;
-  if (active) {
-    const double* __restrict__ src = cx.W + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc;
+  long long dst[PK_LIST_CHUNK];
 #pragma unroll
-    for (int l = 0; l < PK_LIST_CHUNK; ++l) sv[l] = src[lists[2 * (l < nl ? l : 0) + 1]];
-    w = cx.dpool[jb.i[8] + K];
+  for (int l = 0; l < PK_LIST_CHUNK; ++l) {
+    const int ll = l < nl ? l : 0;
+    dst[l] = lists[2 * ll];
+    sv[l] = src[lists[2 * ll + 1]];
   }
+  const double w = cx.dpool[jb.i[8] + K];
+  const double* u = unit_s + cc;
   const bool use_lam = jb.flags & PK_F_LAM;
   const double* lam = cx.LAM + (long long)b * cx.m + jb.i[2] + (long long)K * rows;
-  const int total = nKb * bn;
-  __syncthreads();
-  for (int l = 0; l < nl; ++l) {
-    if (active) {
-      double* tcol = tile + Kl * bn + cc;
-      const double* u = unit_s + cc;
-      const double s = sv[l];
-#pragma unroll 4
-      for (int r = 0; r < rows; ++r) {
-        double v = (u[r * n] * w) / 2.0;
+  for (int r0 = 0; r0 < rows; r0 += PK_ROW_TILE) {
+    double a[PK_ROW_TILE];
+#pragma unroll
+    for (int j = 0; j < PK_ROW_TILE; ++j) {
+      const int r = r0 + j;
+      double v = 0.0;
+      if (r < rows) {
+        v = (u[r * n] * w) / 2.0;
         if (use_lam) v = v * lam[r];
-        tcol[r * n] = v * s;
+      }
+      a[j] = v;
+    }
+#pragma unroll
+    for (int l = 0; l < PK_LIST_CHUNK; ++l) {
+      if (l < nl) {
+        double* o = out + dst[l] + (long long)r0 * n;
+#pragma unroll
+        for (int j = 0; j < PK_ROW_TILE; ++j)
+          if (r0 + j < rows) o[j * n] = a[j] * sv[l];
       }
     }
-    __syncthreads();
-    double* out = cx.OUT + (long long)b * cx.n_out + lists[2 * l] + (long long)K0 * bn;
-    const int head = (int)((reinterpret_cast<unsigned long long>(out) >> 3) & 1);  // 0: 16-byte aligned
-    if (head == 0) {
-      const int pairs = total >> 1;
-      for (int q = threadIdx.x; q < pairs; q += PK_THREADS)
-        reinterpret_cast<double2*>(out)[q] = reinterpret_cast<const double2*>(tile)[q];
-      if ((total & 1) && threadIdx.x == 0) out[total - 1] = tile[total - 1];
-    } else {
-      for (int q = threadIdx.x; q < total; q += PK_THREADS) out[q] = tile[q];
-    }
-    __syncthreads();
   }
 }
 

@@ -422,7 +422,7 @@ class ModePlan:
                             i2=(lam + piece["row0"]) if has_lam else -1,
                             i3=piece["n"], i4=piece["rows"], i5=piece["step"], i6=piece["c0"],
                             i7=piece["unit"], i8=piece["width"], i10=col.L_m,
-                            i11=piece["count"] // (piece["rows"] * piece["n"]),
+                            i11=piece["count"] // piece["rows"],
                         )
                         rec["lists"] = []
                         self.expand_groups[key] = rec
@@ -514,7 +514,7 @@ class DevicePlan:
             kind="table", k0=k0, count=k1 - k0, row=P.int(Im.row[k0:k1]), col=P.int(Im.col[k0:k1]),
             data=P.dbl(Im.data[k0:k1]),
         )
-        if not (col.same_order and col.dense_blocks and nK >= 3 and n <= 64):
+        if not (col.same_order and col.dense_blocks and nK >= 3):
             return [table(0, len(Im))] if len(Im) else []
         bn = rows * n
         # first interval loses its front column, the last one (LGL) its back column

@@ -214,7 +214,7 @@ class HostEmu:
         sign = jb["f"][0]
         n, rows, step, c0 = i[3], i[4], i[5], i[6]
         bn = n * rows
-        nK = i[11]
+        nK = i[11] // n
         e = np.arange(nK * bn)
         K, rem = e // bn, e % bn
         r, cc = rem // n, rem % n
