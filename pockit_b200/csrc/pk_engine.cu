@@ -42,12 +42,14 @@ struct ModeState {
   double *S = nullptr, *W = nullptr;  // scalar / node tables of this mode (modes may run concurrently)
   cudaStream_t stream = nullptr;      // used when a whole evaluation set is launched at once
   cudaEvent_t done = nullptr;
+  cudaStream_t side = nullptr;        // the small slot runs overlap the block expansion
+  cudaEvent_t side_fork = nullptr, side_join = nullptr;
   std::vector<char> cubin;
   pk_job* jobs[PK_N_STAGES] = {};
   long long n_jobs[PK_N_STAGES] = {};
   // block -> (job, chunk) maps of the two slot-streaming kernels
   int* gen_job = nullptr; int* gen_chunk = nullptr; long long gen_blocks = 0;
-  int* exp_job = nullptr; int* exp_chunk = nullptr; long long exp_blocks = 0;
+  long long* exp_prefix = nullptr; long long exp_blocks = 0; int exp_uniform = 0;
   size_t exp_smem = 0;
   long long max_defect_rows = 0, max_grad_count = 0, max_reduce_len = 0;
   size_t def_smem = 0;
@@ -131,14 +133,16 @@ static void free_mode(ModeState& ms) {
   }
   if (ms.gen_job) cudaFree(ms.gen_job);
   if (ms.gen_chunk) cudaFree(ms.gen_chunk);
-  if (ms.exp_job) cudaFree(ms.exp_job);
-  if (ms.exp_chunk) cudaFree(ms.exp_chunk);
+  if (ms.exp_prefix) cudaFree(ms.exp_prefix);
   if (ms.lib) cudaLibraryUnload(ms.lib);
   if (ms.OUT) cudaFree(ms.OUT);
   if (ms.S) cudaFree(ms.S);
   if (ms.W) cudaFree(ms.W);
   if (ms.stream) cudaStreamDestroy(ms.stream);
   if (ms.done) cudaEventDestroy(ms.done);
+  if (ms.side) cudaStreamDestroy(ms.side);
+  if (ms.side_fork) cudaEventDestroy(ms.side_fork);
+  if (ms.side_join) cudaEventDestroy(ms.side_join);
   if (ms.red_partial) cudaFree(ms.red_partial);
   if (ms.red_ticket) cudaFree(ms.red_ticket);
   ms = ModeState();
@@ -214,7 +218,6 @@ static int build_block_map(const pk_job* jobs, long long n, int field, int per, 
   std::vector<int> bj, bc;
   for (long long j = 0; j < n; ++j) {
     long long chunks = (jobs[j].i[field] + per - 1) / per;
-    if (field == 11) chunks *= (jobs[j].i[1] + PK_LIST_CHUNK - 1) / PK_LIST_CHUNK;  // expand: x list chunks
     for (long long c = 0; c < chunks; ++c) {
       bj.push_back((int)j);
       bc.push_back((int)c);
@@ -265,6 +268,9 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     CK(cudaMemset(ms.S, 0, ns));
     CK(cudaStreamCreateWithFlags(&ms.stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ms.side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ms.side_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ms.side_join, cudaEventDisableTiming));
   }
   if (e->set_graph) {  // a re-loaded mode invalidates the captured set
     cudaGraphExecDestroy(e->set_graph);
@@ -279,16 +285,33 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     }
   }
   if (build_block_map(d->jobs[PK_STAGE_GENERIC], d->n_jobs[PK_STAGE_GENERIC], 1, PK_CHUNK, &ms.gen_job, &ms.gen_chunk, &ms.gen_blocks)) return 1;
-  if (build_block_map(d->jobs[PK_STAGE_EXPAND], d->n_jobs[PK_STAGE_EXPAND], 11, PK_THREADS, &ms.exp_job, &ms.exp_chunk, &ms.exp_blocks)) return 1;
-  for (long long j = 0; j < d->n_jobs[PK_STAGE_EXPAND]; ++j) {
-    const pk_job& jb = d->jobs[PK_STAGE_EXPAND][j];
-    const size_t sm = sizeof(double) * (size_t)(jb.i[3] * jb.i[4]);
-    if (sm > ms.exp_smem) ms.exp_smem = sm;
-    if (jb.i[11] >= (1LL << 31)) return fail("expand job with more than 2^31 (interval, column) pairs");
-  }
-  if (ms.exp_smem > 48 * 1024) {
-    if (ms.exp_smem > 200 * 1024) return fail("integration block too large for shared memory");
-    CK(cudaFuncSetAttribute(pk_expand_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.exp_smem));
+  if (d->n_jobs[PK_STAGE_EXPAND] > 0) {
+    const pk_job* ej = d->jobs[PK_STAGE_EXPAND];
+    std::vector<long long> prefix(1, 0);
+    ms.exp_uniform = 1;
+    for (long long j = 0; j < d->n_jobs[PK_STAGE_EXPAND]; ++j) {
+      const pk_job& jb = ej[j];
+      if (jb.i[11] >= (1LL << 31) || jb.i[1] * jb.i[11] >= (1LL << 32)) return fail("expand job too large for 32-bit unit indices");
+      prefix.push_back(prefix.back() + jb.i[1] * jb.i[11]);
+      const size_t sm = sizeof(double) * (size_t)(jb.i[3] * jb.i[4]);
+      if (sm > ms.exp_smem) ms.exp_smem = sm;
+      if (jb.i[7] != ej[0].i[7] || jb.i[3] != ej[0].i[3] || jb.i[4] != ej[0].i[4] || jb.f[0] != ej[0].f[0]) ms.exp_uniform = 0;
+    }
+    if (!ms.exp_uniform) ms.exp_smem = 0;
+    if (ms.exp_smem > 200 * 1024) { ms.exp_uniform = 0; ms.exp_smem = 0; }
+    if (ms.exp_smem > 48 * 1024)
+      CK(cudaFuncSetAttribute(pk_expand_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.exp_smem));
+    CK(cudaMalloc((void**)&ms.exp_prefix, sizeof(long long) * prefix.size()));
+    CK(cudaMemcpy(ms.exp_prefix, prefix.data(), sizeof(long long) * prefix.size(), cudaMemcpyHostToDevice));
+    // one resident wave: SMs x blocks/SM, shared between the instances of a batch
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_expand_blocks, PK_THREADS, ms.exp_smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    long long wave = (long long)(per_sm > 0 ? per_sm : 1) * sms;
+    long long need = (prefix.back() + PK_THREADS - 1) / PK_THREADS;
+    long long gx = (wave + e->dims.batch - 1) / e->dims.batch;
+    if (gx < 1) gx = 1;
+    ms.exp_blocks = need < gx ? need : gx;
   }
   for (long long j = 0; j < d->n_jobs[PK_STAGE_DEFECT]; ++j) {
     const pk_job& jb = d->jobs[PK_STAGE_DEFECT][j];
@@ -385,12 +408,23 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
       ++e->launches;
     }
   }
-  if ((stage_mask & (1u << PK_STAGE_GENERIC)) && ms.gen_blocks) {
+  const bool run_gen = (stage_mask & (1u << PK_STAGE_GENERIC)) && ms.gen_blocks;
+  const bool run_exp = (stage_mask & (1u << PK_STAGE_EXPAND)) && ms.exp_blocks;
+  if (run_gen && run_exp) {
+    // independent of each other (both only read the tables): the latency-bound small runs go to a
+    // side stream and overlap the HBM-bound block expansion
+    CK(cudaEventRecord(ms.side_fork, st));
+    CK(cudaStreamWaitEvent(ms.side, ms.side_fork, 0));
+    pk_generic_jobs<<<dim3((unsigned)ms.gen_blocks, B), PK_THREADS, 0, ms.side>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk);
+    CK(cudaEventRecord(ms.side_join, ms.side));
+    pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], (int)ms.n_jobs[PK_STAGE_EXPAND], ms.exp_prefix, ms.exp_uniform);
+    CK(cudaStreamWaitEvent(st, ms.side_join, 0));
+    e->launches += 2;
+  } else if (run_gen) {
     pk_generic_jobs<<<dim3((unsigned)ms.gen_blocks, B), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk);
     ++e->launches;
-  }
-  if ((stage_mask & (1u << PK_STAGE_EXPAND)) && ms.exp_blocks) {
-    pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], ms.exp_job, ms.exp_chunk);
+  } else if (run_exp) {
+    pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], (int)ms.n_jobs[PK_STAGE_EXPAND], ms.exp_prefix, ms.exp_uniform);
     ++e->launches;
   }
   if (mode == PK_MODE_GRADIENT && (stage_mask & ((1u << PK_STAGE_GRAD_RANGE) | (1u << PK_STAGE_GRAD_SCALAR)))) {

@@ -211,70 +211,49 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const 
 // entries are (unit[r][c] * width_K) / 2 -- the reference's `I_lgl(n) * d / 2` -- so the operator
 // never has to be read from memory: the (sign-folded) unit block sits in shared memory.
 // A job covers ALL lists of one state (they share the block geometry and the multiplier rows).
-// One thread owns one (interval, column) pair = one node and PK_LIST_CHUNK lists: it loads the
-// node's list values first (independent loads), then builds PK_ROW_TILE entries of its coefficient
-// column, (unit*w)/2 [* lam_r], at a time and streams them against the list values; consecutive
-// lanes write runs of n consecutive slots.
-#define PK_ROW_TILE 4
-#define PK_LIST_CHUNK 2
-__global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const pk_job* __restrict__ jobs,
-                                                              const int* __restrict__ blk_job,
-                                                              const int* __restrict__ blk_chunk) {
+// Work unit = (list, interval, column): one node of one list.  The kernel is PERSISTENT: the grid
+// is exactly one resident wave (SMs x blocks/SM) and walks the flattened unit space of all jobs
+// with a grid stride, so every SM streams stores until the very end (no partial last wave).
+// A unit loads its node's list value once and walks down the block column: consecutive lanes
+// write runs of n consecutive slots, ~6 instructions per 8-byte store.
+// prefix[j] = first unit of job j; i11 = (interval, column) pairs of the job.
+__global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs,
+                                                              const long long* __restrict__ prefix, int uniform) {
   extern __shared__ double unit_s[];
-  const pk_job& jb = jobs[blk_job[blockIdx.x]];
   const int b = blockIdx.y;
-  const int n = (int)jb.i[3], rows = (int)jb.i[4];
-  const int bn = n * rows;
-  const double* unit = cx.dpool + jb.i[7];
-  const double sign = jb.f[0];
-  for (int t = threadIdx.x; t < bn; t += PK_THREADS) unit_s[t] = sign * unit[t];  // exact: sign is +-1
-  __syncthreads();
-  // chunk = list_chunk * pair_chunks + pair_chunk
-  const unsigned pairs = (unsigned)jb.i[11];
-  const unsigned pair_chunks = (pairs + PK_THREADS - 1) / PK_THREADS;
-  const unsigned chunk = (unsigned)blk_chunk[blockIdx.x];
-  const unsigned lc = chunk / pair_chunks;
-  const unsigned t = (chunk - lc * pair_chunks) * PK_THREADS + threadIdx.x;
-  if (t >= pairs) return;
-  const unsigned K = t / (unsigned)n;
-  const unsigned cc = t - K * (unsigned)n;
-  const long long* __restrict__ lists = cx.ipool + jb.i[0] + 2 * (long long)lc * PK_LIST_CHUNK;  // (dst, W row base)
-  const int nl = min((int)jb.i[1] - (int)lc * PK_LIST_CHUNK, PK_LIST_CHUNK);
-  const double* __restrict__ src = cx.W + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc;
-  double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + (long long)K * bn + cc;
-  // the node's value in every list of this chunk: independent loads, issued before any store
-  double sv[PK_LIST_CHUNK];
-  long long dst[PK_LIST_CHUNK];
-#pragma unroll
-  for (int l = 0; l < PK_LIST_CHUNK; ++l) {
-    const int ll = l < nl ? l : 0;
-    dst[l] = lists[2 * ll];
-    sv[l] = src[lists[2 * ll + 1]];
+  if (uniform) {  // all jobs share one unit block and sign: keep it (sign folded, exact) in shared memory
+    const pk_job& j0 = jobs[0];
+    const int bn0 = (int)(j0.i[3] * j0.i[4]);
+    const double* unit = cx.dpool + j0.i[7];
+    for (int t = threadIdx.x; t < bn0; t += PK_THREADS) unit_s[t] = j0.f[0] * unit[t];
+    __syncthreads();
   }
-  const double w = cx.dpool[jb.i[8] + K];
-  const double* u = unit_s + cc;
-  const bool use_lam = jb.flags & PK_F_LAM;
-  const double* lam = cx.LAM + (long long)b * cx.m + jb.i[2] + (long long)K * rows;
-  for (int r0 = 0; r0 < rows; r0 += PK_ROW_TILE) {
-    double a[PK_ROW_TILE];
-#pragma unroll
-    for (int j = 0; j < PK_ROW_TILE; ++j) {
-      const int r = r0 + j;
-      double v = 0.0;
-      if (r < rows) {
-        v = (u[r * n] * w) / 2.0;
-        if (use_lam) v = v * lam[r];
-      }
-      a[j] = v;
-    }
-#pragma unroll
-    for (int l = 0; l < PK_LIST_CHUNK; ++l) {
-      if (l < nl) {
-        double* o = out + dst[l] + (long long)r0 * n;
-#pragma unroll
-        for (int j = 0; j < PK_ROW_TILE; ++j)
-          if (r0 + j < rows) o[j * n] = a[j] * sv[l];
-      }
+  const long long total = prefix[n_jobs];
+  int j = 0;
+  for (long long uidx = blockIdx.x * (long long)PK_THREADS + threadIdx.x; uidx < total;
+       uidx += (long long)gridDim.x * PK_THREADS) {
+    while (uidx >= prefix[j + 1]) ++j;
+    const pk_job& jb = jobs[j];
+    const int n = (int)jb.i[3], rows = (int)jb.i[4];
+    const unsigned pairs = (unsigned)jb.i[11];
+    const unsigned v = (unsigned)(uidx - prefix[j]);
+    const unsigned l = v / pairs;
+    const unsigned t = v - l * pairs;
+    const unsigned K = t / (unsigned)n;
+    const unsigned cc = t - K * (unsigned)n;
+    const long long* __restrict__ lists = cx.ipool + jb.i[0] + 2 * (long long)l;  // (dst, W row base)
+    const double sv = cx.W[lists[1] + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc];
+    const double w = cx.dpool[jb.i[8] + K];
+    double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + lists[0] + (long long)K * (n * rows) + cc;
+    const double* u = (uniform ? unit_s : cx.dpool + jb.i[7]) + cc;
+    const double sgn = uniform ? 1.0 : jb.f[0];
+    if (jb.flags & PK_F_LAM) {
+      const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + jb.i[2] + (long long)K * rows;
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) out[r * n] = (((sgn * u[r * n]) * w) / 2.0 * lam[r]) * sv;
+    } else {
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) out[r * n] = (((sgn * u[r * n]) * w) / 2.0) * sv;
     }
   }
 }
