@@ -214,10 +214,10 @@ static int compile(const pk_mode_desc* d, int device, std::vector<char>& cubin) 
   return 0;
 }
 
-static int build_block_map(const pk_job* jobs, long long n, int field, int per, int** d_job, int** d_chunk, long long* n_blocks) {
+static int build_block_map(const pk_job* jobs, long long n, int field, int per, long long batch, int** d_job, int** d_chunk, long long* n_blocks) {
   std::vector<int> bj, bc;
   for (long long j = 0; j < n; ++j) {
-    long long chunks = (jobs[j].i[field] + per - 1) / per;
+    long long chunks = (jobs[j].i[field] * batch + per - 1) / per;
     for (long long c = 0; c < chunks; ++c) {
       bj.push_back((int)j);
       bc.push_back((int)c);
@@ -284,7 +284,7 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
       CK(cudaMemcpy(ms.jobs[s], d->jobs[s], sizeof(pk_job) * (size_t)d->n_jobs[s], cudaMemcpyHostToDevice));
     }
   }
-  if (build_block_map(d->jobs[PK_STAGE_GENERIC], d->n_jobs[PK_STAGE_GENERIC], 1, PK_CHUNK, &ms.gen_job, &ms.gen_chunk, &ms.gen_blocks)) return 1;
+  if (build_block_map(d->jobs[PK_STAGE_GENERIC], d->n_jobs[PK_STAGE_GENERIC], 1, PK_CHUNK, e->dims.batch, &ms.gen_job, &ms.gen_chunk, &ms.gen_blocks)) return 1;
   if (d->n_jobs[PK_STAGE_EXPAND] > 0) {
     const pk_job* ej = d->jobs[PK_STAGE_EXPAND];
     std::vector<long long> prefix(1, 0);
@@ -415,13 +415,13 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
     // side stream and overlap the HBM-bound block expansion
     CK(cudaEventRecord(ms.side_fork, st));
     CK(cudaStreamWaitEvent(ms.side, ms.side_fork, 0));
-    pk_generic_jobs<<<dim3((unsigned)ms.gen_blocks, B), PK_THREADS, 0, ms.side>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk);
+    pk_generic_jobs<<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ms.side>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
     CK(cudaEventRecord(ms.side_join, ms.side));
     pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], (int)ms.n_jobs[PK_STAGE_EXPAND], ms.exp_prefix, ms.exp_uniform);
     CK(cudaStreamWaitEvent(st, ms.side_join, 0));
     e->launches += 2;
   } else if (run_gen) {
-    pk_generic_jobs<<<dim3((unsigned)ms.gen_blocks, B), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk);
+    pk_generic_jobs<<<(unsigned)ms.gen_blocks, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
     ++e->launches;
   } else if (run_exp) {
     pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], (int)ms.n_jobs[PK_STAGE_EXPAND], ms.exp_prefix, ms.exp_uniform);

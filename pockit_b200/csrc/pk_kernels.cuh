@@ -266,25 +266,29 @@ __device__ __forceinline__ double pk_list_at(const PkCtx& cx, const double* Sb, 
   return cx.W[src + (long long)b * lm + c_lo + k];
 }
 
+// The (instance, slot) space of a job is flattened: idx = b * count + e, so that batches of small
+// problems (runs of a few dozen slots) still fill whole warps; consecutive lanes write consecutive
+// slots of a run and continue in the next instance's run.
 __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk_job* __restrict__ jobs,
                                                              const int* __restrict__ blk_job,
-                                                             const int* __restrict__ blk_chunk) {
+                                                             const int* __restrict__ blk_chunk, int B) {
   const pk_job& jb = jobs[blk_job[blockIdx.x]];
-  const int b = blockIdx.y;
-  const double* Sb = cx.S + (long long)b * cx.n_scalar;
-  const double* lam = cx.LAM + (long long)b * cx.m;
-  double* out = cx.OUT + (long long)b * cx.n_out + jb.i[0];
   const long long count = jb.i[1];
+  const long long total = count * B;
   const double sign = jb.f[0];
   const bool use_lam = jb.flags & PK_F_LAM;
-  const double sysv = jb.i[3] >= 0 ? Sb[jb.i[3]] : 1.0;
-  double post = 1.0;
-  if (jb.i[4] == 1) post = cx.SIG[b];
-  if (jb.i[4] == 2) post = lam[jb.i[5]];
-  const long long e0 = (long long)blk_chunk[blockIdx.x] * PK_CHUNK + threadIdx.x;
+  const long long i0 = (long long)blk_chunk[blockIdx.x] * PK_CHUNK + threadIdx.x;
   for (int it = 0; it < PK_ITEMS; ++it) {
-    const long long e = e0 + (long long)it * PK_THREADS;
-    if (e >= count) break;
+    const long long idx = i0 + (long long)it * PK_THREADS;
+    if (idx >= total) break;
+    const int b = (int)(idx / count);
+    const long long e = idx - (long long)b * count;
+    const double* Sb = cx.S + (long long)b * cx.n_scalar;
+    const double* lam = cx.LAM + (long long)b * cx.m;
+    const double sysv = jb.i[3] >= 0 ? Sb[jb.i[3]] : 1.0;
+    double post = 1.0;
+    if (jb.i[4] == 1) post = cx.SIG[b];
+    if (jb.i[4] == 2) post = lam[jb.i[5]];
     double v;
     switch (jb.type) {
       case PK_JOB_CONST:
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
         if (jb.i[4]) v = v * post;
       }
     }
-    out[e] = v;
+    cx.OUT[(long long)b * cx.n_out + jb.i[0] + e] = v;
   }
 }
 
