@@ -55,6 +55,7 @@ struct ModeState {
   size_t def_smem = 0;
   double* red_partial = nullptr; unsigned* red_ticket = nullptr; int red_parts = 0;
   bool def_fast = false, def_table = false;
+  bool idx32 = true;  // every flattened (instance, slot) space fits 32-bit index math
 };
 
 struct pk_engine {
@@ -327,7 +328,8 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
   }
   if (ms.def_smem > 48 * 1024) {
     if (ms.def_smem > 200 * 1024) return fail("integration block too large for shared memory");
-    CK(cudaFuncSetAttribute(pk_defects_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.def_smem));
+    CK(cudaFuncSetAttribute(pk_defects_blocks<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.def_smem));
+    CK(cudaFuncSetAttribute(pk_defects_blocks<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.def_smem));
   }
   for (long long j = 0; j < d->n_jobs[PK_STAGE_REDUCE]; ++j) {
     const long long len = d->jobs[PK_STAGE_REDUCE][j].i[3] - d->jobs[PK_STAGE_REDUCE][j].i[2];
@@ -342,6 +344,12 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
   }
   for (long long j = 0; j < d->n_jobs[PK_STAGE_GRAD_RANGE]; ++j)
     if (d->jobs[PK_STAGE_GRAD_RANGE][j].i[1] > ms.max_grad_count) ms.max_grad_count = d->jobs[PK_STAGE_GRAD_RANGE][j].i[1];
+  {
+    const long long lim = 1LL << 31, B = e->dims.batch;
+    for (long long j = 0; j < d->n_jobs[PK_STAGE_GENERIC]; ++j)
+      if (d->jobs[PK_STAGE_GENERIC][j].i[1] * B >= lim) ms.idx32 = false;
+    if (ms.max_defect_rows * B >= lim || ms.max_grad_count * B >= lim) ms.idx32 = false;
+  }
   ms.loaded = true;
   return 0;
 }
@@ -404,7 +412,10 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
       ++e->launches;
     }
     if (ms.def_fast) {
-      pk_defects_blocks<<<grid, PK_THREADS, ms.def_smem, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+      if (ms.idx32)
+        pk_defects_blocks<unsigned><<<grid, PK_THREADS, ms.def_smem, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+      else
+        pk_defects_blocks<unsigned long long><<<grid, PK_THREADS, ms.def_smem, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
       ++e->launches;
     }
   }
@@ -415,13 +426,19 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
     // side stream and overlap the HBM-bound block expansion
     CK(cudaEventRecord(ms.side_fork, st));
     CK(cudaStreamWaitEvent(ms.side, ms.side_fork, 0));
-    pk_generic_jobs<<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ms.side>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
+    if (ms.idx32)
+      pk_generic_jobs<unsigned><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ms.side>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
+    else
+      pk_generic_jobs<unsigned long long><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ms.side>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
     CK(cudaEventRecord(ms.side_join, ms.side));
     pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], (int)ms.n_jobs[PK_STAGE_EXPAND], ms.exp_prefix, ms.exp_uniform);
     CK(cudaStreamWaitEvent(st, ms.side_join, 0));
     e->launches += 2;
   } else if (run_gen) {
-    pk_generic_jobs<<<(unsigned)ms.gen_blocks, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
+    if (ms.idx32)
+      pk_generic_jobs<unsigned><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
+    else
+      pk_generic_jobs<unsigned long long><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
     ++e->launches;
   } else if (run_exp) {
     pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], (int)ms.n_jobs[PK_STAGE_EXPAND], ms.exp_prefix, ms.exp_uniform);
@@ -431,7 +448,10 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
     CK(cudaMemsetAsync(ms.OUT, 0, sizeof(double) * (size_t)B * (size_t)ms.n_out, st));
     if (ms.n_jobs[PK_STAGE_GRAD_RANGE]) {
       dim3 grid(blocks_for(ms.max_grad_count * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_GRAD_RANGE]);
-      pk_grad_range<<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
+      if (ms.idx32)
+        pk_grad_range<unsigned><<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
+      else
+        pk_grad_range<unsigned long long><<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
       ++e->launches;
     }
     if (ms.n_jobs[PK_STAGE_GRAD_SCALAR]) {

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects(PkCtx cx, const pk_job*
 // Same-order meshes: the operator is never read from memory.  i13 = n (points per interval),
 // flags = rows per block (= node step = offset of the -1 column: n-1 for LGL, n for LGR),
 // i14 dpool unit block (rows x n), i15 dpool interval widths.  Entries are (unit * width) / 2.
+template <typename IT>  // unsigned (fast 32-bit index math) whenever rows * n_x * B < 2^32
 __global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
   extern __shared__ double unit_s[];
   const pk_job& jb = jobs[blockIdx.y];
@@ -179,31 +180,31 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const 
   const double* unit = cx.dpool + jb.i[14];
   for (int t = threadIdx.x; t < rb * n; t += PK_THREADS) unit_s[(t / n) * ld + (t % n)] = unit[t];
   __syncthreads();
-  const long long rows = jb.i[4], n_x = jb.i[3];
-  const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
-  if (gid >= rows * n_x * B) return;
+  const IT rows = (IT)jb.i[4], n_x = (IT)jb.i[3];
+  const IT gid = (IT)blockIdx.x * (IT)PK_THREADS + threadIdx.x;
+  if (gid >= rows * n_x * (IT)B) return;
   const int b = (int)(gid / (rows * n_x));
-  const long long rem = gid - (long long)b * rows * n_x;
+  const IT rem = gid - (IT)b * rows * n_x;
   const int i = (int)(rem / rows);
-  const long long r = rem - (long long)i * rows;
-  const long long K = r / rb;
-  const int rr = (int)(r - K * rb);
+  const IT r = rem - (IT)i * rows;
+  const IT K = r / (IT)rb;
+  const int rr = (int)(r - K * (IT)rb);
   const long long Lx = jb.i[1], Lm = jb.i[2];
   const double* Sb = cx.S + (long long)b * cx.n_scalar + jb.i[11];
   const double* xv = cx.X + (long long)b * cx.L + jb.i[0] + (long long)i * Lx;
-  const double* f = cx.W + jb.i[10] + ((long long)i * B + b) * Lm + K * rb;
+  const double* f = cx.W + jb.i[10] + ((long long)i * B + b) * Lm + (long long)K * rb;
   const double w = cx.dpool[jb.i[15] + K];
   const double* u = unit_s + rr * ld;
   double acc = 0.0;
 #pragma unroll 4
   for (int c = 0; c < n; ++c) acc += ((u[c] * w) / 2.0) * f[c];
-  const long long cp = K * rb + rr, cn = K * rb + rb;
+  const long long cp = (long long)K * rb + rr, cn = (long long)K * rb + rb;
   const double xp = cp == 0 ? Sb[1 + i] : (cp == Lx - 1 ? Sb[1 + n_x + i] : xv[cp]);
   const double xn = cn == 0 ? Sb[1 + i] : (cn == Lx - 1 ? Sb[1 + n_x + i] : xv[cn]);
   double tx = 0.0;
   tx += 1.0 * xp;
   tx += -1.0 * xn;
-  cx.OUT[(long long)b * cx.n_out + jb.i[12] + (long long)i * rows + r] = tx - acc * Sb[0];
+  cx.OUT[(long long)b * cx.n_out + jb.i[12] + (long long)i * (long long)rows + (long long)r] = tx - acc * Sb[0];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -269,20 +270,21 @@ __device__ __forceinline__ double pk_list_at(const PkCtx& cx, const double* Sb, 
 // The (instance, slot) space of a job is flattened: idx = b * count + e, so that batches of small
 // problems (runs of a few dozen slots) still fill whole warps; consecutive lanes write consecutive
 // slots of a run and continue in the next instance's run.
+template <typename IT>  // unsigned whenever every job has count * B < 2^32
 __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk_job* __restrict__ jobs,
                                                              const int* __restrict__ blk_job,
                                                              const int* __restrict__ blk_chunk, int B) {
   const pk_job& jb = jobs[blk_job[blockIdx.x]];
-  const long long count = jb.i[1];
-  const long long total = count * B;
+  const IT count = (IT)jb.i[1];
+  const IT total = count * (IT)B;
   const double sign = jb.f[0];
   const bool use_lam = jb.flags & PK_F_LAM;
-  const long long i0 = (long long)blk_chunk[blockIdx.x] * PK_CHUNK + threadIdx.x;
+  const IT i0 = (IT)blk_chunk[blockIdx.x] * (IT)PK_CHUNK + threadIdx.x;
   for (int it = 0; it < PK_ITEMS; ++it) {
-    const long long idx = i0 + (long long)it * PK_THREADS;
+    const IT idx = i0 + (IT)it * PK_THREADS;
     if (idx >= total) break;
     const int b = (int)(idx / count);
-    const long long e = idx - (long long)b * count;
+    const IT e = idx - (IT)b * count;
     const double* Sb = cx.S + (long long)b * cx.n_scalar;
     const double* lam = cx.LAM + (long long)b * cx.m;
     const double sysv = jb.i[3] >= 0 ? Sb[jb.i[3]] : 1.0;
@@ -295,8 +297,8 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
         v = cx.dpool[jb.i[6] + e];
         break;
       case PK_JOB_KRON: {
-        const long long nb = jb.i[7];
-        const long long a = e / nb, q = e - a * nb;
+        const IT nb = (IT)jb.i[7];
+        const IT a = e / nb, q = e - a * nb;
         double d = cx.dpool[jb.i[6] + a];
         if (use_lam) d = d * lam[cx.ipool[jb.i[9] + a]];
         v = sign * (d * Sb[jb.i[8] + q]);
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
         v = d * cx.W[jb.i[9] + (long long)b * jb.i[10] + cx.ipool[jb.i[7] + e]];
       } break;
       case PK_JOB_SCALED:
-        v = pk_list_at(cx, Sb, b, jb.flags & PK_F_A_SCALAR, 0, jb.i[6], jb.i[7], jb.i[8], e) * sysv;
+        v = pk_list_at(cx, Sb, b, jb.flags & PK_F_A_SCALAR, 0, jb.i[6], jb.i[7], jb.i[8], (long long)e) * sysv;
         if (jb.i[4]) v = v * post;
         break;
       case PK_JOB_SYS:
@@ -317,13 +319,13 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
       default: {  // OUTER / TRIL
         long long ia, ib;
         if (jb.type == PK_JOB_OUTER) {
-          ia = e / jb.i[12];
-          ib = e - ia * jb.i[12];
+          ia = (long long)(e / (IT)jb.i[12]);
+          ib = (long long)e - ia * jb.i[12];
         } else {
           ia = (long long)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
           while (ia * (ia + 1) / 2 > e) --ia;
           while ((ia + 1) * (ia + 2) / 2 <= e) ++ia;
-          ib = e - ia * (ia + 1) / 2;
+          ib = (long long)e - ia * (ia + 1) / 2;
         }
         const double va = pk_list_at(cx, Sb, b, jb.flags & PK_F_A_SCALAR, jb.flags & PK_F_A_UNIT, jb.i[6], jb.i[7], jb.i[8], ia);
         const double vb = pk_list_at(cx, Sb, b, jb.flags & PK_F_B_SCALAR, jb.flags & PK_F_B_UNIT, jb.i[9], jb.i[10], jb.i[11], ib);
@@ -331,18 +333,20 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
         if (jb.i[4]) v = v * post;
       }
     }
-    cx.OUT[(long long)b * cx.n_out + jb.i[0] + e] = v;
+    cx.OUT[(long long)b * cx.n_out + jb.i[0] + (long long)e] = v;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // gradient: each output column sums its contributions in list order (np.add.at semantics)
+template <typename IT>
 __global__ void __launch_bounds__(PK_THREADS) pk_grad_range(PkCtx cx, const pk_job* __restrict__ jobs, int B) {
   const pk_job& jb = jobs[blockIdx.y];
-  const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
-  if (gid >= jb.i[1] * B) return;
-  const int b = (int)(gid / jb.i[1]);
-  const long long e = gid - (long long)b * jb.i[1];
+  const IT cnt = (IT)jb.i[1];
+  const IT gid = (IT)blockIdx.x * (IT)PK_THREADS + threadIdx.x;
+  if (gid >= cnt * (IT)B) return;
+  const int b = (int)(gid / cnt);
+  const long long e = (long long)(gid - (IT)b * cnt);
   const double* Sb = cx.S + (long long)b * cx.n_scalar;
   const long long* q = cx.ipool + jb.i[2];
   double acc = 0.0;
