@@ -290,6 +290,11 @@ def main():
     n_mid = lo.phases[0].L_m
     alg_bytes = 8 * (slots + rows * n_mid + lo.phases[0].col.n_rows * lo.phases[0].n_x)
     achieved = alg_bytes / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else 0.0
+    traffic = None
+    tr = ROOT / "profiles" / "r01_expand_traffic.json"
+    if tr.exists():  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (Hessian launch)
+        rec = json.loads(tr.read_text())["launches"][-1]
+        traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
     set_bytes = 8 * (6 * L + 2 * m + nj + nh)
     per_mode = {}
     for mname, mm in zip(("objective", "gradient", "constraints", "jacobian", "hessian"), modes):
@@ -306,7 +311,7 @@ def main():
         },
         "roofline": {
             "bound": "hbm", "kernel": "pk_expand_blocks (Hessian mode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": exp_ms,
         },
         "e2e": {"value": world * args.steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
