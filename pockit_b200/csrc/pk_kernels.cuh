@@ -233,6 +233,13 @@ __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const p
   int j = 0;
   for (long long uidx = blockIdx.x * (long long)PK_THREADS + threadIdx.x; uidx < total;
        uidx += (long long)gridDim.x * PK_THREADS) {
+    if (n_jobs > 8 && uidx >= prefix[j + 1]) {  // many runs (hp-refined mesh): binary search
+      int hi = n_jobs;
+      while (hi - j > 1) {
+        const int mid = (j + hi) >> 1;
+        if (uidx >= prefix[mid]) j = mid; else hi = mid;
+      }
+    }
     while (uidx >= prefix[j + 1]) ++j;
     const pk_job& jb = jobs[j];
     const int n = (int)jb.i[3], rows = (int)jb.i[4];

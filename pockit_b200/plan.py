@@ -501,38 +501,58 @@ class DevicePlan:
         )
 
     def _expand_pieces(self, p):
-        """Split the middle part of the integration operator into runs the EXPAND
-        kernel can address arithmetically (interior intervals of a mesh whose
-        intervals all have the same order) and table-driven remainders."""
+        """Split the middle part of the integration operator into pieces the EXPAND kernel can
+        address arithmetically -- maximal runs of complete interval blocks of equal order (an
+        hp-refined mesh gives several runs) -- and table-driven remainders (the first interval
+        loses its front column, the last LGL interval its back column, and blocks that lost an
+        exact zero are irregular)."""
+        from .discretization import _unit_integration_block
+
         col = p.col
         Im = col.I.m
         P = self.pools
         nK = len(col.num_point)
-        n = int(col.num_point[0])
-        rows = n - 1 if col.scheme == "lgl" else n
+        lgl = col.scheme == "lgl"
+        npt = col.num_point.astype(np.int64)
+        off = np.searchsorted(Im.row, col.row_start)  # first triplet of every interval (+ end)
         table = lambda k0, k1: dict(
-            kind="table", k0=k0, count=k1 - k0, row=P.int(Im.row[k0:k1]), col=P.int(Im.col[k0:k1]),
+            kind="table", k0=int(k0), count=int(k1 - k0), row=P.int(Im.row[k0:k1]), col=P.int(Im.col[k0:k1]),
             data=P.dbl(Im.data[k0:k1]),
         )
-        if not (col.same_order and col.dense_blocks and nK >= 3):
-            return [table(0, len(Im))] if len(Im) else []
-        bn = rows * n
-        # first interval loses its front column, the last one (LGL) its back column
-        head = int(np.searchsorted(Im.row, rows))  # triplets of interval 0
-        tail0 = int(np.searchsorted(Im.row, rows * (nK - 1)))
-        assert tail0 - head == bn * (nK - 2)
-        from .discretization import _unit_integration_block
+        width_off = P.dbl(col.width)
+        pieces, pending = [], None  # pending = start of the current table stretch
 
-        unit = _unit_integration_block(col.scheme, n)
-        step = n - 1 if col.scheme == "lgl" else n
-        pieces = [table(0, head)]
-        pieces.append(
-            dict(
-                kind="block", k0=head, count=tail0 - head, n=n, rows=rows, step=step, c0=int(col.l_m[1]),
-                row0=rows, unit=P.dbl(unit.ravel()), width=P.dbl(col.width) + 1,
+        def flush(k_end):
+            nonlocal pending
+            if pending is not None and k_end > pending:
+                pieces.append(table(pending, k_end))
+            pending = None
+
+        K = 0
+        while K < nK:
+            n = int(npt[K])
+            rows = n - 1 if lgl else n
+            complete = K > 0 and not (lgl and K == nK - 1) and off[K + 1] - off[K] == rows * n and n <= 128
+            if not complete:
+                if pending is None:
+                    pending = int(off[K])
+                K += 1
+                continue
+            Kb = K
+            while (
+                Kb < nK and npt[Kb] == n and not (lgl and Kb == nK - 1) and off[Kb + 1] - off[Kb] == rows * n
+            ):
+                Kb += 1
+            flush(int(off[K]))
+            unit = _unit_integration_block(col.scheme, n)
+            pieces.append(
+                dict(
+                    kind="block", k0=int(off[K]), count=int(off[Kb] - off[K]), n=n, rows=rows, step=rows,
+                    c0=int(col.l_m[K]), row0=int(col.row_start[K]), unit=P.dbl(unit.ravel()), width=width_off + K,
+                )
             )
-        )
-        pieces.append(table(tail0, len(Im)))
+            K = Kb
+        flush(len(Im))
         return [q for q in pieces if q["count"]]
 
     # ---------------------------------------------------------------- code generation

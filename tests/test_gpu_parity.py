@@ -41,6 +41,9 @@ def test_callbacks_match_reference_golden(case):
         ("quadrotor", "lobatto", dict(mesh=14, num_point=6)),
         ("humanoid", "lobatto", dict(mesh=20, num_point=10)),
         ("lqr", "radau", dict(mesh=[0, 0.1, 0.15, 0.4, 0.7, 1.0], num_point=[4, 7, 3, 9, 5])),
+        # hp-refined style meshes: runs of equal order -> several block pieces, mixed unit blocks
+        ("robot_arm", "radau", dict(mesh=24, num_point=[3] * 5 + [6] * 7 + [4] * 3 + [9] * 6 + [5, 3, 3])),
+        ("rocket", "lobatto", dict(mesh=20, num_point=[4] * 6 + [7] * 8 + [3, 5, 5, 5, 8, 8])),
     ],
 )
 def test_callbacks_match_oracle(builder, scheme, kw):
