@@ -258,8 +258,6 @@ class Phase:
         if np.any(npt > np.iinfo(np.int32).max):
             raise ValueError("num_point entries are too large")
         col = Collocation(self._scheme, mesh_new, npt.astype(np.int32), self.n_x, self.n_u)
-        if col.index_mstage.L_m < 1:
-            raise ValueError("the mesh must contain at least one interior collocation node")
         self.col = col
         self._mesh, self._num_interval, self._num_point = mesh_new, n_int, npt.astype(np.int32)
         self._discretization_set = True

@@ -288,6 +288,8 @@ class ModePlan:
         ranges: dict = {}
         scalars: dict = {}
         for sg in lo.grad_segments:
+            if sg.count == 0:
+                continue
             g = self.sys_slot(sg.sys)
             if sg.kind == "sys":
                 scalars.setdefault(int(sg.cols[0]), []).append((-1, g))
@@ -298,7 +300,7 @@ class ModePlan:
                 continue
             row = self.row_of(pi, "mid", sg.term, True)
             c_lo = lo.low[pi].mid_lo
-            if sg.count > 1 and sg.cols[0] == sg.cols[-1]:  # broadcast column: np.add.at accumulates
+            if sg.count == 1 or sg.cols[0] == sg.cols[-1]:  # one column: np.add.at accumulates into it
                 slot = self.new_slot()
                 self.job(ST_REDUCE, i0=("row", row), i1=p.L_m, i2=c_lo, i3=c_lo + sg.count, i4=slot)
                 scalars.setdefault(int(sg.cols[0]), []).append((slot, g))
@@ -329,6 +331,8 @@ class ModePlan:
         lo, own = self.owner.lo, self.owner
         dst = 0
         for sg in segs:
+            if sg.count == 0:
+                continue
             if sg.kind == "phase":
                 self._phase_run(sg, dst)
             elif sg.kind == "sys":

@@ -15,7 +15,8 @@ import numpy as np
 import sympy as sp
 
 __all__ = [
-    "lqr", "robot_arm", "humanoid", "rocket", "quadrotor", "general", "evaluation_point", "BUILDERS",
+    "lqr", "robot_arm", "humanoid", "rocket", "quadrotor", "general", "static_only", "no_control", "tiny",
+    "evaluation_point", "BUILDERS",
 ]
 
 
@@ -244,7 +245,43 @@ def general(mod, mesh=(0, 0.2, 1), num_point=(3, 4), linear_objective=False):
     return S
 
 
+def static_only(mod):
+    """No phase at all: objective and system constraints of static parameters only
+    (``tests/test_base/test_system_base.py:11-19`` in the reference)."""
+    S = mod.System(2)
+    S.set_objective(S.s[0] ** 2 * sp.cos(S.s[1]) + S.s[1])
+    S.set_system_constraint([S.s[0] * S.s[1], S.s[0]], [0, -1], [1, 1])
+    return S
+
+
+def no_control(mod, mesh=3, num_point=3):
+    """A phase without controls, FUNC terminal value, explicit time dependence."""
+    S = mod.System(1)
+    p = S.new_phase(2, 0)
+    p.set_dynamics([p.x[1], -p.x[0] * S.s[0] + p.t])
+    p.set_boundary_condition([1.0, None], [None, S.s[0] ** 2], 0.0, 2.0)
+    p.set_integral([p.x[0] ** 2])
+    p.set_discretization(mesh, num_point)
+    S.set_phase([p])
+    S.set_objective(p.I[0] + S.s[0])
+    return S
+
+
+def tiny(mod, mesh=1, num_point=3):
+    """Smallest meshes: one or two intervals, middle node sets of length 0 or 1."""
+    S = mod.System(0)
+    p = S.new_phase(1, 1)
+    p.set_dynamics([p.x[0] * p.u[0]])
+    p.set_boundary_condition([1.0], [None], 0.0, None)
+    p.set_integral([p.u[0] ** 2 + p.x[0]])
+    p.set_discretization(mesh, num_point)
+    S.set_phase([p])
+    S.set_objective(p.I[0])
+    return S
+
+
 BUILDERS = {
+    "static_only": static_only, "no_control": no_control, "tiny": tiny,
     "lqr": lqr, "robot_arm": robot_arm, "humanoid": humanoid, "rocket": rocket,
     "quadrotor": quadrotor, "general": general,
 }

@@ -33,6 +33,12 @@ CASES = {
     "rocket_lgl_4x5": ("rocket", "lobatto", {"mesh": 4, "num_point": 5}),
     "rocket_lgr_3x3": ("rocket", "radau", {"mesh": 3, "num_point": 3}),
     "quadrotor_lgl_14x6": ("quadrotor", "lobatto", {"mesh": 14, "num_point": 6}),
+    "static_only_lgl": ("static_only", "lobatto", {}),
+    "no_control_lgl_3x3": ("no_control", "lobatto", {}),
+    "no_control_lgr_3x3": ("no_control", "radau", {}),
+    "tiny_lgl_1x3": ("tiny", "lobatto", {"mesh": 1, "num_point": 3}),
+    "tiny_lgl_2x2": ("tiny", "lobatto", {"mesh": 2, "num_point": 2}),
+    "tiny_lgr_1x2": ("tiny", "radau", {"mesh": 1, "num_point": 2}),
     "quadrotor_lgr_5x3": ("quadrotor", "radau", {"mesh": [0, 0.1, 0.3, 0.6, 0.8, 1.0], "num_point": [3, 4, 3, 5, 2]}),
 }
 
