@@ -283,18 +283,29 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     iters = 20
     _, stages = eng.time(P.HESS, iters=iters, stages=True)
-    exp_ms = stages[P.ST_EXPAND] / iters
-    jobs = eng.fin[P.HESS]["jobs"][P.ST_EXPAND]
-    slots = int(sum(int(j["i"][1]) * int(j["i"][11]) * int(j["i"][4]) for j in jobs))  # lists x pairs x block rows
-    rows = int(sum(int(j["i"][1]) for j in jobs))
-    n_mid = lo.phases[0].L_m
-    alg_bytes = 8 * (slots + rows * n_mid + lo.phases[0].col.n_rows * lo.phases[0].n_x)
-    achieved = alg_bytes / (exp_ms * 1e-3) / 1e9 if exp_ms > 0 else 0.0
+    fin = eng.fin[P.HESS]
+    if len(fin["jobs"][P.ST_EXPAND]):  # table/W path (irregular blocks): the stand-alone expansion kernel dominates
+        kernel = "pk_expand_blocks (Hessian mode)"
+        k_ms = stages[P.ST_EXPAND] / iters
+        jobs = fin["jobs"][P.ST_EXPAND]
+        slots = int(sum(int(j["i"][1]) * int(j["i"][11]) * int(j["i"][4]) for j in jobs))
+        rows_read = int(sum(int(j["i"][1]) for j in jobs))
+        alg_bytes = 8 * (slots + rows_read * lo.phases[0].L_m + lo.phases[0].col.n_rows * lo.phases[0].n_x)
+    else:  # fused path: the generated per-node program evaluates, chains and writes the slots itself
+        kernel = "pk_node_hessian_p0 (NVRTC per-node program with fused block expansion)"
+        k_ms = stages[6] / iters
+        small = int(sum(int(j["i"][1]) for j in fin["jobs"][P.ST_GENERIC]))
+        slots = lo.nnz_hess_o + lo.nnz_hess_c - small
+        rows_written = len(eng.plan.mode(P.HESS).rows)
+        # slots written + x and multipliers read once + node-table rows written
+        alg_bytes = 8 * (slots + lo.r_s + lo.m + rows_written * lo.phases[0].L_m)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     tr = ROOT / "profiles" / "r01_expand_traffic.json"
-    if tr.exists():  # DRAM bytes of the same kernel from the committed `ncu --set full` capture (Hessian launch)
-        rec = json.loads(tr.read_text())["launches"][-1]
-        traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
+    if tr.exists():  # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture
+        recs = [r for r in json.loads(tr.read_text())["launches"] if r["kernel"].split(" ")[0] == kernel.split(" ")[0]]
+        if recs:
+            traffic = recs[-1]["dram_read_bytes"] + recs[-1]["dram_write_bytes"]
     set_bytes = 8 * (6 * L + 2 * m + nj + nh)
     per_mode = {}
     for mname, mm in zip(("objective", "gradient", "constraints", "jacobian", "hessian"), modes):
@@ -310,9 +321,9 @@ def main():
             "ms_per_callback": per_mode,
         },
         "roofline": {
-            "bound": "hbm", "kernel": "pk_expand_blocks (Hessian mode)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": exp_ms,
+            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_ms,
         },
         "e2e": {"value": world * args.steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1000.0 * e2e_t / args.steps, "ms_per_callback": e2e_each, "outputs": "page-locked engine buffers (System.pinned_outputs=True)"},

@@ -384,7 +384,7 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
       const double* tm = e->dpool + np_.tm_offset;
       const double* wm = e->dpool + np_.wm_offset;
       int Bi = B;
-      void* args[] = {&e->X, &e->LAM, &e->FIX, &tm, &wm, &ms.S, &ms.W, &ms.OUT, &Bi};
+      void* args[] = {&e->X, &e->LAM, &e->FIX, &tm, &wm, &ms.S, &ms.W, &ms.OUT, &Bi, &e->dpool, &e->ipool};
       const long long threads = (long long)B * np_.n_nodes;
       CK(cudaLaunchKernel((void*)ms.node_kernels[p], dim3(blocks_for(threads, 128)), dim3(128), args, 0, st));
       ++e->launches;

@@ -19,6 +19,30 @@ __device__ __forceinline__ double pk_sq(double v) { return v * v; }
 __device__ __forceinline__ double pk_cube(double v) { return v * v * v; }
 __device__ __forceinline__ double pk_sign(double v) { return (v > 0.0) - (v < 0.0); }
 __device__ __forceinline__ double pk_heaviside(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? 0.0 : 0.5); }
+
+// One column of one interval block of the integration operator, as seen by the node that owns it:
+// entries (unit[r][c] * width) / 2 for r = 0..rows-1 land `stride` slots apart, starting at `off`.
+struct PkColumn { const double* u; double w; long long off; long long row0; int n, rows, stride; };
+__device__ __forceinline__ PkColumn pk_column(const double* DP, const long long* rec, int cc, double width) {
+    PkColumn k;
+    k.n = (int)rec[0]; k.rows = (int)rec[1]; k.stride = (int)rec[2];
+    k.u = DP + rec[6] + cc; k.w = width;
+    k.off = rec[5] + (cc - rec[3]); k.row0 = rec[7];
+    return k;
+}
+// slots of one list in that column: sign * ((unit * w) / 2) [* lam_row] * v, the reference's association
+__device__ __forceinline__ void pk_walk(double* __restrict__ o, double v, const PkColumn& k,
+                                        const double* __restrict__ lam, double sign) {
+    o += k.off;
+    if (lam) {
+        lam += k.row0;
+#pragma unroll 4
+        for (int r = 0; r < k.rows; ++r) o[(long long)r * k.stride] = ((((sign * k.u[r * k.n]) * k.w) / 2.0) * lam[r]) * v;
+    } else {
+#pragma unroll 4
+        for (int r = 0; r < k.rows; ++r) o[(long long)r * k.stride] = (((sign * k.u[r * k.n]) * k.w) / 2.0) * v;
+    }
+}
 """
 
 _UNARY = {

@@ -108,6 +108,7 @@ class PhaseProgram:
     s_store: dict = field(default_factory=dict)  # (nset, code) -> scalar slot
     w_store: dict = field(default_factory=dict)  # (nset, code) -> table row id
     direct: list = field(default_factory=list)  # (nset, code, dst, lam or -1, c_lo)
+    walks: list = field(default_factory=list)  # (code, dst, lam row base or -1, sign): fused block expansion
 
 
 class ModePlan:
@@ -406,6 +407,11 @@ class ModePlan:
                 ST_GENERIC, J_KRON, flags, f0=seg.sign, i0=dst, i1=seg.count, i2=-1, i3=-1,
                 i6=pools.dbl(seg.data), i7=nb, i8=first, i9=rows_off,
             )
+        elif seg.kind == "expand" and own.walk_tables[pi] is not None:
+            t = seg.terms[0]
+            self._track(pi, t)
+            lam = sg.lam_base + seg.lam_off if has_lam else -1
+            self.prog[pi].walks.append((term_code(t), dst, lam, seg.sign))
         elif seg.kind == "expand":
             row = self.row_of(pi, "mid", seg.terms[0])
             lam = sg.lam_base + seg.lam_off if has_lam else -1
@@ -468,6 +474,7 @@ class DevicePlan:
         self.wm_off = [self.pools.dbl(p.col.w_m) for p in lo.phases]
         self.defect_tables = [self._defect_tables(p) for p in lo.phases]
         self.expand_pieces = [self._expand_pieces(p) for p in lo.phases]
+        self.walk_tables = [self._walk_tables(p) for p in lo.phases]
         self.modes: dict[int, ModePlan] = {}
 
     def mode(self, m: int) -> ModePlan:
@@ -503,6 +510,36 @@ class DevicePlan:
         return dict(
             row_ptr=P.int(row_ptr), col=P.int(cols), data=P.dbl(data), tpos=P.int(tpos), tneg=P.int(tneg), **fast
         )
+
+    def _walk_tables(self, p):
+        """Per-interval geometry for the FUSED expansion (the per-node program itself walks down
+        its column of the interval block and writes the slots): for interval K
+        ``[n, rows, row length of its middle part, first kept column, first node, first triplet,
+        dpool offset of the unit block, first defect row]`` plus the node -> interval map.
+        ``None`` when a block lost an exact zero (slot arithmetic would be off): table path."""
+        from .discretization import _unit_integration_block
+
+        col = p.col
+        if not col.dense_blocks or p.n_x == 0:
+            return None
+        Im = col.I.m
+        nK = len(col.num_point)
+        lgl = col.scheme == "lgl"
+        off = np.searchsorted(Im.row, col.row_start)
+        rec = np.zeros((nK, 8), dtype=np.int64)
+        node_iv = np.zeros(col.L_m, dtype=np.int64)
+        for K in range(nK):
+            n = int(col.num_point[K])
+            rows = n - 1 if lgl else n
+            first = 1 if K == 0 else 0
+            length = n - first - (1 if lgl and K == nK - 1 else 0)
+            if rows * length != off[K + 1] - off[K]:
+                return None
+            unit = _unit_integration_block(col.scheme, n)
+            rec[K] = [n, rows, length, first, col.l_m[K], off[K], self.pools.dbl(unit.ravel()), col.row_start[K]]
+            node_iv[col.l_m[K] : col.r_m[K]] = K  # LGL border nodes end up in the interval they start
+        return dict(node_iv=self.pools.int(node_iv), rec=self.pools.int(rec.ravel()), width=self.pools.dbl(col.width),
+                    lgl=lgl)
 
     def _expand_pieces(self, p):
         """Split the middle part of the integration operator into pieces the EXPAND kernel can
@@ -628,7 +665,8 @@ class DevicePlan:
         A(f'extern "C" __global__ void __launch_bounds__({NODE_BLOCK}) {kname}(')
         A("    const double* __restrict__ X, const double* __restrict__ LAM, const double* __restrict__ FIX,")
         A("    const double* __restrict__ TM, const double* __restrict__ WM,")
-        A("    double* __restrict__ S, double* __restrict__ W, double* __restrict__ OUT, int B)")
+        A("    double* __restrict__ S, double* __restrict__ W, double* __restrict__ OUT, int B,")
+        A("    const double* __restrict__ DP, const long long* __restrict__ IP)")
         A("{")
         A(f"    const long long* T = pk_tab_{name};")
         A(f"    const int Lm = (int){T(col.L_m)};")
@@ -729,6 +767,26 @@ class DevicePlan:
             L += stores("back", "        ")
         A("    } else {")
         L += stores("mid", "        ")
+        if prog.walks:
+            wt = self.walk_tables[pi]
+            A("        // fused expansion through the integration operator: this node's column of its")
+            A("        // interval block (two columns for a shared LGL border node), phasebase.py:1120-1124, 1280-1285")
+            A(f"        const int K = (int)IP[{T(wt['node_iv'])} + c];")
+            A(f"        const long long* rk = IP + {T(wt['rec'])} + 8LL * K;")
+            A("        const int cc = c - (int)rk[4];")
+            A(f"        const PkColumn col0 = pk_column(DP, rk, cc, DP[{T(wt['width'])} + K]);")
+            if wt["lgl"]:
+                A("        const bool shared = (cc == 0 && K > 0);")
+                A("        const long long* rj = shared ? rk - 8 : rk;")
+                A(f"        const PkColumn col1 = pk_column(DP, rj, (int)rj[0] - 1, DP[{T(wt['width'])} + (shared ? K - 1 : K)]);")
+            for code, dst, lam, sign in prog.walks:
+                lam0 = "nullptr" if lam < 0 else f"lam + {T(lam)}"
+                A(f"        {{ const double v = {code}; double* o = out + {T(dst)}; const double* lm = {lam0};")
+                A(f"          pk_walk(o, v, col0, lm, {sign!r});")
+                if wt["lgl"]:
+                    A(f"          if (shared) pk_walk(o, v, col1, lm, {sign!r}); }}")
+                else:
+                    A("        }")
         A("    }")
         A("    if (last) {")
         for i in range(n_x):

@@ -37,10 +37,11 @@ def _compile(source: str, kernels, sys_kernel):
     for k in kernels:
         drivers.append(
             f'extern "C" void run_{k}(const double* X, const double* LAM, const double* FIX, const double* TM,'
-            f" const double* WM, double* S, double* W, double* OUT, int B, long long threads) {{\n"
+            f" const double* WM, double* S, double* W, double* OUT, int B, const double* DP, const long long* IP,"
+            f" long long threads) {{\n"
             f"  blockDim.x = 128;\n"
             f"  for (long long g = 0; g < threads; ++g) {{ blockIdx.x = g / 128; threadIdx.x = g % 128;\n"
-            f"    {k}(X, LAM, FIX, TM, WM, S, W, OUT, B); }}\n}}\n"
+            f"    {k}(X, LAM, FIX, TM, WM, S, W, OUT, B, DP, IP); }}\n}}\n"
         )
     if sys_kernel:
         drivers.append(
@@ -101,7 +102,7 @@ class HostEmu:
             wm = self.dpool[dp.wm_off[pi] : dp.wm_off[pi] + Lm].copy()
             getattr(lib, "run_" + k)(
                 _ptr(X), _ptr(LAM), _ptr(FIX), _ptr(tm), _ptr(wm), _ptr(S), _ptr(W), _ptr(OUT),
-                ctypes.c_int(B), ctypes.c_longlong(B * Lm),
+                ctypes.c_int(B), _ptr(self.dpool), _ptr(self.ipool), ctypes.c_longlong(B * Lm),
             )
         jobs = f["jobs"]
         for jb in jobs[P.ST_REDUCE]:
