@@ -130,7 +130,7 @@ class Engine:
         self.lib = load_library()
         self.lowering = lowering
         self.B = int(batch)
-        self.plan = P.DevicePlan(lowering, self.B, fastmath)
+        self.plan = P.DevicePlan(lowering, self.B, fastmath, fused=os.environ.get("POCKIT_B200_FUSED", "0") == "1")
         self.fin = {}
         for m in range(N_MODES):
             self.plan.mode(m)

@@ -448,10 +448,16 @@ class ModePlan:
 class DevicePlan:
     """Pools + per-mode plans for one lowered system."""
 
-    def __init__(self, lo: SystemLowering, batch: int = 1, fastmath: bool = False):
+    def __init__(self, lo: SystemLowering, batch: int = 1, fastmath: bool = False, fused: bool = False):
         self.lo = lo
         self.B = int(batch)
         self.fastmath = fastmath
+        # fused=True: the per-node program itself walks its block column and writes the slots (no
+        # node-table round trip, one launch less).  Measured on B200 (round 1) it is SLOWER than the
+        # node program + persistent pk_expand_blocks pair (robot_arm Hessian 40 us vs 31 us, humanoid
+        # 100k nodes 254 us vs 159 us per set): one thread per node is too little parallelism for
+        # hundreds of serial stores.  Kept selectable (and tested) as the base for a multi-thread-per-node version.
+        self.fused = bool(fused)
         self.pools = Pools()
         # scalar-table header: per phase [dt, front values (n_x), back values (n_x)]
         self.header = []
@@ -474,7 +480,7 @@ class DevicePlan:
         self.wm_off = [self.pools.dbl(p.col.w_m) for p in lo.phases]
         self.defect_tables = [self._defect_tables(p) for p in lo.phases]
         self.expand_pieces = [self._expand_pieces(p) for p in lo.phases]
-        self.walk_tables = [self._walk_tables(p) for p in lo.phases]
+        self.walk_tables = [self._walk_tables(p) if self.fused else None for p in lo.phases]
         self.modes: dict[int, ModePlan] = {}
 
     def mode(self, m: int) -> ModePlan:

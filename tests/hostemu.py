@@ -67,9 +67,9 @@ def _ptr(a):
 
 
 class HostEmu:
-    def __init__(self, system, batch=1, fixed=None):
+    def __init__(self, system, batch=1, fixed=None, fused=False):
         self.lo = system.lowering
-        self.dp = P.DevicePlan(self.lo, batch)
+        self.dp = P.DevicePlan(self.lo, batch, fused=fused)
         self.B = batch
         for m in range(5):
             self.dp.mode(m)

@@ -28,3 +28,14 @@ def test_values_match_reference(case):
     assert_close(E.run(P.HESS, x, lam, sigma), g["hessian"], "hessian")
     n_o = len(g["hessian_o"])
     assert_close(E.run(P.HESS, x, np.zeros_like(lam), 1.0)[:n_o], g["hessian_o"], "hessian_o")
+
+
+@pytest.mark.parametrize("name", ["general_lgl", "robot_arm_lgr_6x20", "rocket_lgl_4x5", "quadrotor_lgr_5x3", "tiny_lgl_2x2"])
+def test_fused_expansion_variant_matches_reference(name):
+    """DevicePlan(fused=True): the per-node program writes the expanded slots itself."""
+    S, g = build(name), load(name)
+    E = HostEmu(S, fused=True)
+    assert all(len(E.fin[m]["jobs"][P.ST_EXPAND]) == 0 for m in (P.JAC, P.HESS))
+    x, lam, sigma = g["x"], g["lam"], float(g["sigma"])
+    assert_close(E.run(P.JAC, x), g["jacobian"], "jacobian")
+    assert_close(E.run(P.HESS, x, lam, sigma), g["hessian"], "hessian")
