@@ -193,8 +193,13 @@ static int compile(const pk_mode_desc* d, int device, std::vector<char>& cubin) 
   // B200 is sm_100: compile for the arch-specific target; anything else gets its own real arch
   std::string arch = "--gpu-architecture=sm_" + std::to_string(prop.major * 10 + prop.minor) +
                      ((prop.major == 10 && prop.minor == 0) ? "a" : "");
-  std::vector<const char*> opts = {arch.c_str(), "--std=c++17", "-lineinfo", "--fmad=false"};
-  for (int i = 0; i < d->n_nvrtc_options; ++i) opts.push_back(d->nvrtc_options[i]);
+  std::vector<const char*> opts = {arch.c_str(), "--std=c++17", "-lineinfo"};
+  bool fmad_given = false;  // strict IEEE products by default; a fastmath model passes --fmad=true
+  for (int i = 0; i < d->n_nvrtc_options; ++i) {
+    if (strncmp(d->nvrtc_options[i], "--fmad", 6) == 0 || strncmp(d->nvrtc_options[i], "-fmad", 5) == 0) fmad_given = true;
+    opts.push_back(d->nvrtc_options[i]);
+  }
+  if (!fmad_given) opts.push_back("--fmad=false");
   nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   if (r != NVRTC_SUCCESS) {
     size_t n = 0;

@@ -150,3 +150,17 @@ def test_evaluation_set_graph_matches_single_callbacks():
     eng.sync()
     for m in modes:
         assert np.array_equal(np.atleast_1d(eng.download(m)), single[m]), P.MODES[m]
+
+
+def test_fastmath_model_compiles_and_stays_close():
+    """fastmath=True (the reference passes it to Numba; here it maps to --fmad=true): results may
+    differ in the last bits but must stay within a few ulp of the strict evaluation."""
+    import pockit_b200.lobatto as lob
+    from pockit_b200 import problems
+
+    strict = problems.quadrotor(lob, fastmath=False)
+    fast = problems.quadrotor(lob, fastmath=True)
+    x, lam, sigma = problems.evaluation_point(strict)
+    np.testing.assert_allclose(fast.jacobian(x), strict.jacobian(x), rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(fast.hessian(x, lam, sigma), strict.hessian(x, lam, sigma), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(fast.constraints(x), strict.constraints(x), rtol=1e-13, atol=1e-13)
