@@ -11,9 +11,11 @@ nnz_J=12 479 754, nnz_H=12 799 740).
 
 * ``value``  device-resident throughput: inputs already in HBM, CUDA events on the
   engine's stream around each step, L2 flushed (untimed) between steps.
-* ``e2e``    the same metric through the public API (System.objective / gradient /
-  constraints / jacobian / hessian) with HOST buffers: every step copies x (and
-  lambda, sigma) to the device and all five results back.
+* ``e2e``    the same metric through the public API with HOST buffers: every step copies
+  x, lambda, sigma to the device and all five results back.  ``e2e.value`` uses the
+  single-call set evaluation (System.evaluate -> pk_eval_set: one upload, copies
+  overlapped with compute); ``e2e.five_callbacks`` is the same set through the five
+  reference-style callbacks called one after the other (x uploaded five times).
 * ``roofline`` the dominant kernel (pk_expand_blocks of the Hessian) against the
   measured HBM copy bandwidth in MEASURED_PEAKS.json.
 * ``cpu_baseline`` / ``--impl reference``: the CPU oracle port (oracle/pockit_oracle.py,
@@ -178,6 +180,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-compact", action="store_true", help="skip the extra de-duplicated-pattern measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,21 +246,27 @@ def main():
     def one_set():
         S.objective(x); S.gradient(x); S.constraints(x); S.jacobian(x); S.hessian(x, lam, sigma)
 
-    for _ in range(max(3, args.warmup)):
-        one_set()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_set()
-    torch.cuda.synchronize()
-    e2e_local = time.perf_counter() - t0
+    def one_set_call():
+        S.evaluate(x, lam, sigma)
+
+    def timed_host(fn):
+        for _ in range(max(3, args.warmup)):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        torch.cuda.synchronize()
+        t_loc = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([t_loc], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return t_loc
+
+    e2e_five_t = timed_host(one_set)
+    e2e_t = timed_host(one_set_call)
     clk.__exit__()
-    if dist is not None:
-        t = torch.tensor([e2e_local], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_t = float(t.item())
-    else:
-        e2e_t = e2e_local
     e2e_each = {}
     for cname, fn in (("objective", lambda: S.objective(x)), ("gradient", lambda: S.gradient(x)),
                       ("constraints", lambda: S.constraints(x)), ("jacobian", lambda: S.jacobian(x)),
@@ -267,8 +276,25 @@ def main():
             fn()
         e2e_each[cname] = 1000.0 * (time.perf_counter() - t0) / 5
     L, m, nj, nh = lo.r_s, lo.m, lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c
-    h2d = 8 * (5 * L + m + 1)
+    h2d = 8 * (L + m + 1)
     d2h = 8 * (1 + L + m + nj + nh)
+    # opt-in de-duplicated patterns (outside the reference's pattern contract; reported beside it)
+    compact = None
+    if rank == 0 and not args.no_compact:
+        S.compact_patterns = True
+        cj, ch = len(S.jacobianstructure()[0]), len(S.hessianstructure()[0])
+        for _ in range(3):
+            one_set_call()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one_set_call()
+        tc = (time.perf_counter() - t0) / args.steps
+        dev_ms = eng.time_steps(modes, min(args.steps, 20), flush_l2=True)
+        compact = {"note": "System.compact_patterns=True: duplicates summed on the device, unique (row, col) pairs only",
+                   "nnz_jac": cj, "nnz_hess": ch, "e2e_eval_sets_per_s": 1.0 / tc, "e2e_ms_per_step": 1000.0 * tc,
+                   "d2h_bytes_per_step": 8 * (1 + L + m + cj + ch),
+                   "device_resident_ms_per_step": sum(dev_ms) / len(dev_ms)}
+        S.compact_patterns = False
 
     if rank != 0:
         if dist is not None:
@@ -276,10 +302,13 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ----------------------------------------------------
-    peaks = {}
-    pk = ROOT / "MEASURED_PEAKS.json"
-    if pk.exists():
-        peaks = json.loads(pk.read_text())
+    peaks, peak_source = {}, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+    for pk, label in ((ROOT / "MEASURED_PEAKS.json", "MEASURED_PEAKS.json"),
+                      (ROOT / "profiles" / "r01_measured_peaks.json",
+                       "profiles/r01_measured_peaks.json (copy of the driver's round-1 MEASURED_PEAKS.json)")):
+        if pk.exists():
+            peaks, peak_source = json.loads(pk.read_text()), label
+            break
     peak = float(peaks.get("hbm_gbs", 6650.0))
     iters = 20
     _, stages = eng.time(P.HESS, iters=iters, stages=True)
@@ -322,14 +351,21 @@ def main():
         },
         "roofline": {
             "bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_source,
             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": k_ms,
         },
         "e2e": {"value": world * args.steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1000.0 * e2e_t / args.steps, "ms_per_callback": e2e_each, "outputs": "page-locked engine buffers (System.pinned_outputs=True)"},
+                "ms_per_step": 1000.0 * e2e_t / args.steps,
+                "api": "System.evaluate(x, lam, sigma) -> pk_eval_set: one upload, per-mode streams, copies overlapped",
+                "five_callbacks": {"value": world * args.steps / e2e_five_t, "ms_per_step": 1000.0 * e2e_five_t / args.steps,
+                                   "h2d_bytes_per_step": 8 * (5 * L + m + 1), "ms_per_callback": e2e_each,
+                                   "api": "System.objective/gradient/constraints/jacobian/hessian one after the other"},
+                "outputs": "page-locked engine buffers (System.pinned_outputs=True)"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
+    if compact is not None:
+        line["config"]["compact_patterns"] = compact
     if not args.no_cpu_baseline and world == 1:
         v, worst = cpu_eval_sets_per_s(1, 3)
         line["cpu_baseline"] = {

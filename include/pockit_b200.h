@@ -132,6 +132,27 @@ int pk_eval_jacobian(pk_engine *e, const double *x, double *values /* [B][nnz_ja
 int pk_eval_hessian(pk_engine *e, const double *x, const double *lambda /* [B][m] */,
                     const double *sigma /* [B] */, double *values /* [B][nnz_hess] */);
 
+/* All requested callbacks at one x in a single call (the "evaluate the whole set at this x" entry
+ * point of an x-keyed cache in a solver adapter; Ipopt asks for f, grad f, g, J, H at the same x,
+ * optimizer/ipopt.py:41-53): x and the multipliers cross PCIe once, the modes run concurrently and
+ * every result is copied back as soon as its mode finishes.  outs[k] receives mode modes[k];
+ * lambda / sigma are only read when PK_MODE_HESSIAN is among the modes. */
+int pk_eval_set(pk_engine *e, const double *x, const double *lambda, const double *sigma, const int *modes,
+                int n_modes, double *const *outs);
+
+/* ---- optional output shaping (both leave the reference pattern contract when enabled) ----
+ * Mesh sharding (one fine mesh split over several GPUs): this engine was given only a
+ * share of the slot-run jobs; `runs` = n_runs (offset, count) pairs of the output it computes.
+ * pk_download / pk_eval_* then copy just those runs, to the same offsets of the host buffer
+ * (a buffer shared by all ranks ends up complete).  n_runs = 0 restores the full copy. */
+int pk_engine_set_output_runs(pk_engine *e, int mode, const int64_t *runs, int64_t n_runs);
+/* De-duplicated pattern: the reference's COO patterns repeat (row, col) pairs and leave the sum to
+ * the consumer (optimizer/scipy.py:13-29).  With a compaction table the engine sums the duplicates
+ * on the device -- unique entry u = sum of slots perm[seg_ptr[u] .. seg_ptr[u+1]) in that order --
+ * and the callbacks return n_unique values per instance.  n_unique = 0 switches it off. */
+int pk_engine_set_compaction(pk_engine *e, int mode, int64_t n_unique, const int64_t *seg_ptr, const int64_t *perm);
+int pk_out_size(pk_engine *e, int mode, int64_t *n); /* values per instance the host receives for this mode */
+
 /* ---- device-resident path (inputs already in HBM): upload once, run many, download ---- */
 int pk_upload_x(pk_engine *e, const double *x);
 int pk_upload_multipliers(pk_engine *e, const double *lambda, const double *sigma);

@@ -56,6 +56,12 @@ struct ModeState {
   double* red_partial = nullptr; unsigned* red_ticket = nullptr; int red_parts = 0;
   bool def_fast = false, def_table = false;
   bool idx32 = true;  // every flattened (instance, slot) space fits 32-bit index math
+  // mesh sharding: the (offset, count) runs of the output this engine computes; empty = all of it
+  std::vector<long long> dl_runs;
+  // de-duplicated pattern: OUTC[u] = sum of OUT[perm[ptr[u] .. ptr[u+1])]
+  long long n_compact = 0;
+  unsigned *cp_ptr = nullptr, *cp_perm = nullptr;
+  double* OUTC = nullptr;
 };
 
 struct pk_engine {
@@ -63,7 +69,7 @@ struct pk_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   double *X = nullptr, *LAM = nullptr, *SIG = nullptr, *FIX = nullptr;
-  cudaEvent_t fork = nullptr;
+  cudaEvent_t fork = nullptr, x_done = nullptr, lam_done = nullptr;
   cudaGraphExec_t set_graph = nullptr;  // captured evaluation set (all requested modes, one stream each)
   std::vector<int> set_modes;
   double* dpool = nullptr; long long* ipool = nullptr;
@@ -118,6 +124,8 @@ extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   CK(cudaMemsetAsync(e->LAM, 0, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1), e->stream));
   CK(cudaMemsetAsync(e->SIG, 0, sizeof(double) * (size_t)B, e->stream));
   CK(cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->x_done, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->lam_done, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&e->hX, sizeof(double) * (size_t)(B * d->L > 0 ? B * d->L : 1)));
   CK(cudaMallocHost((void**)&e->hLAM, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1)));
   CK(cudaMallocHost((void**)&e->hSIG, sizeof(double) * (size_t)B));
@@ -146,6 +154,9 @@ static void free_mode(ModeState& ms) {
   if (ms.side_join) cudaEventDestroy(ms.side_join);
   if (ms.red_partial) cudaFree(ms.red_partial);
   if (ms.red_ticket) cudaFree(ms.red_ticket);
+  if (ms.cp_ptr) cudaFree(ms.cp_ptr);
+  if (ms.cp_perm) cudaFree(ms.cp_perm);
+  if (ms.OUTC) cudaFree(ms.OUTC);
   ms = ModeState();
 }
 
@@ -157,6 +168,8 @@ extern "C" int pk_engine_destroy(pk_engine* e) {
   cudaFree(e->X); cudaFree(e->LAM); cudaFree(e->SIG);
   if (e->set_graph) cudaGraphExecDestroy(e->set_graph);
   if (e->fork) cudaEventDestroy(e->fork);
+  if (e->x_done) cudaEventDestroy(e->x_done);
+  if (e->lam_done) cudaEventDestroy(e->lam_done);
   cudaFree(e->FIX); cudaFree(e->dpool); cudaFree(e->ipool); cudaFree(e->flush);
   cudaFreeHost(e->hX); cudaFreeHost(e->hLAM); cudaFreeHost(e->hSIG); cudaFreeHost(e->hOUT);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -465,6 +478,11 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
       ++e->launches;
     }
   }
+  if (ms.n_compact && stage_mask == ~0u) {
+    pk_compact<<<blocks_for(ms.n_compact * B, PK_THREADS), PK_THREADS, 0, st>>>(ms.OUT, ms.OUTC, ms.cp_ptr, ms.cp_perm, ms.n_out,
+                                                                               ms.n_compact, B);
+    ++e->launches;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -473,8 +491,10 @@ extern "C" int pk_upload_x(pk_engine* e, const double* x) {
   if (!e || !x) return fail("pk_upload_x: null argument");
   CK(cudaSetDevice(e->device));
   const size_t n = sizeof(double) * (size_t)e->dims.batch * (size_t)e->dims.L;
+  CK(cudaEventSynchronize(e->x_done));  // the previous copy may still be reading the staging buffer
   memcpy(e->hX, x, n);
   CK(cudaMemcpyAsync(e->X, e->hX, n, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaEventRecord(e->x_done, e->stream));
   return 0;
 }
 
@@ -482,6 +502,7 @@ extern "C" int pk_upload_multipliers(pk_engine* e, const double* lambda, const d
   if (!e) return fail("pk_upload_multipliers: null engine");
   CK(cudaSetDevice(e->device));
   const size_t B = (size_t)e->dims.batch;
+  CK(cudaEventSynchronize(e->lam_done));
   if (lambda && e->dims.m > 0) {
     const size_t n = sizeof(double) * B * (size_t)e->dims.m;
     memcpy(e->hLAM, lambda, n);
@@ -491,6 +512,7 @@ extern "C" int pk_upload_multipliers(pk_engine* e, const double* lambda, const d
     memcpy(e->hSIG, sigma, sizeof(double) * B);
     CK(cudaMemcpyAsync(e->SIG, e->hSIG, sizeof(double) * B, cudaMemcpyHostToDevice, e->stream));
   }
+  CK(cudaEventRecord(e->lam_done, e->stream));
   return 0;
 }
 
@@ -506,13 +528,89 @@ extern "C" int pk_sync(pk_engine* e) {
   return 0;
 }
 
+// Enqueue the device-to-host copy of a mode's result on `st`.  `out` may be pinned (pk_alloc_host)
+// or pageable; the runtime handles both.  De-duplicated pattern: the compacted values; mesh
+// sharding: only the runs this engine computed, to the same offsets of `out`.
+static int download_async(pk_engine* e, int mode, double* out, cudaStream_t st) {
+  ModeState& ms = e->mode[mode];
+  const size_t B = (size_t)e->dims.batch;
+  if (ms.n_compact) {
+    CK(cudaMemcpyAsync(out, ms.OUTC, sizeof(double) * B * (size_t)ms.n_compact, cudaMemcpyDeviceToHost, st));
+  } else if (!ms.dl_runs.empty()) {
+    for (size_t b = 0; b < B; ++b)
+      for (size_t r = 0; r + 1 < ms.dl_runs.size(); r += 2) {
+        const size_t off = b * (size_t)ms.n_out + (size_t)ms.dl_runs[r];
+        CK(cudaMemcpyAsync(out + off, ms.OUT + off, sizeof(double) * (size_t)ms.dl_runs[r + 1], cudaMemcpyDeviceToHost, st));
+      }
+  } else {
+    CK(cudaMemcpyAsync(out, ms.OUT, sizeof(double) * B * (size_t)ms.n_out, cudaMemcpyDeviceToHost, st));
+  }
+  return 0;
+}
+
 extern "C" int pk_download(pk_engine* e, int mode, double* out) {
   if (!e || !out || mode < 0 || mode >= PK_N_MODES) return fail("pk_download: bad argument");
   CK(cudaSetDevice(e->device));
-  const size_t n = sizeof(double) * (size_t)e->dims.batch * (size_t)e->mode[mode].n_out;
-  // `out` may be pinned (pk_alloc_host) or pageable; the runtime handles both
-  CK(cudaMemcpyAsync(out, e->mode[mode].OUT, n, cudaMemcpyDeviceToHost, e->stream));
+  if (download_async(e, mode, out, e->stream)) return 1;
   CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+extern "C" int pk_engine_set_output_runs(pk_engine* e, int mode, const int64_t* runs, int64_t n_runs) {
+  if (!e || mode < 0 || mode >= PK_N_MODES || n_runs < 0 || (n_runs && !runs)) return fail("pk_engine_set_output_runs: bad argument");
+  ModeState& ms = e->mode[mode];
+  if (!ms.loaded) return fail("pk_engine_set_output_runs: mode not loaded");
+  if (ms.n_compact && n_runs) return fail("pk_engine_set_output_runs: not available with a de-duplicated pattern");
+  for (int64_t r = 0; r < n_runs; ++r)
+    if (runs[2 * r] < 0 || runs[2 * r + 1] < 0 || runs[2 * r] + runs[2 * r + 1] > ms.n_out)
+      return fail("pk_engine_set_output_runs: run outside the output");
+  ms.dl_runs.assign(runs, runs + 2 * n_runs);
+  return 0;
+}
+
+extern "C" int pk_engine_set_compaction(pk_engine* e, int mode, int64_t n_unique, const int64_t* seg_ptr, const int64_t* perm) {
+  if (!e || mode < 0 || mode >= PK_N_MODES || n_unique < 0) return fail("pk_engine_set_compaction: bad argument");
+  CK(cudaSetDevice(e->device));
+  ModeState& ms = e->mode[mode];
+  if (!ms.loaded) return fail("pk_engine_set_compaction: mode not loaded");
+  if (!ms.dl_runs.empty()) return fail("pk_engine_set_compaction: not available on a mesh shard");
+  if (ms.cp_ptr) cudaFree(ms.cp_ptr);
+  if (ms.cp_perm) cudaFree(ms.cp_perm);
+  if (ms.OUTC) cudaFree(ms.OUTC);
+  ms.cp_ptr = ms.cp_perm = nullptr;
+  ms.OUTC = nullptr;
+  ms.n_compact = 0;
+  if (e->set_graph) {  // the captured set no longer matches
+    cudaGraphExecDestroy(e->set_graph);
+    e->set_graph = nullptr;
+    e->set_modes.clear();
+  }
+  if (n_unique == 0) return 0;
+  if (!seg_ptr || !perm) return fail("pk_engine_set_compaction: null table");
+  if (ms.n_out >= (1LL << 32)) return fail("pk_engine_set_compaction: pattern too large for 32-bit slot indices");
+  if (seg_ptr[0] != 0 || seg_ptr[n_unique] != ms.n_out) return fail("pk_engine_set_compaction: segments must cover every slot once");
+  std::vector<unsigned> p32((size_t)n_unique + 1), q32((size_t)ms.n_out);
+  for (int64_t u = 0; u <= n_unique; ++u) {
+    if (u && seg_ptr[u] < seg_ptr[u - 1]) return fail("pk_engine_set_compaction: segment table not monotone");
+    p32[(size_t)u] = (unsigned)seg_ptr[u];
+  }
+  for (int64_t k = 0; k < ms.n_out; ++k) {
+    if (perm[k] < 0 || perm[k] >= ms.n_out) return fail("pk_engine_set_compaction: slot index out of range");
+    q32[(size_t)k] = (unsigned)perm[k];
+  }
+  CK(cudaMalloc((void**)&ms.cp_ptr, sizeof(unsigned) * p32.size()));
+  CK(cudaMalloc((void**)&ms.cp_perm, sizeof(unsigned) * (q32.size() ? q32.size() : 1)));
+  CK(cudaMalloc((void**)&ms.OUTC, sizeof(double) * (size_t)e->dims.batch * (size_t)n_unique));
+  CK(cudaMemcpy(ms.cp_ptr, p32.data(), sizeof(unsigned) * p32.size(), cudaMemcpyHostToDevice));
+  if (!q32.empty()) CK(cudaMemcpy(ms.cp_perm, q32.data(), sizeof(unsigned) * q32.size(), cudaMemcpyHostToDevice));
+  ms.n_compact = n_unique;
+  return 0;
+}
+
+extern "C" int pk_out_size(pk_engine* e, int mode, int64_t* n) {
+  if (!e || !n || mode < 0 || mode >= PK_N_MODES) return fail("pk_out_size: bad argument");
+  const ModeState& ms = e->mode[mode];
+  *n = ms.n_compact ? ms.n_compact : ms.n_out;
   return 0;
 }
 
@@ -530,6 +628,47 @@ extern "C" int pk_eval_jacobian(pk_engine* e, const double* x, double* v) { retu
 extern "C" int pk_eval_hessian(pk_engine* e, const double* x, const double* lam, const double* sig, double* v) {
   if (!lam || !sig) return fail("pk_eval_hessian: multipliers required");
   return eval(e, PK_MODE_HESSIAN, x, lam, sig, v);
+}
+
+// Host-to-host evaluation of several callbacks at one x: x (and the multipliers) cross PCIe once,
+// every mode runs on its own stream and its device-to-host copy is queued right behind its kernels,
+// so the copies of the large Jacobian / Hessian value arrays overlap the other modes' compute and
+// the host blocks once.  This is the entry point of an x-keyed evaluation cache in a solver adapter
+// (Ipopt asks for f, grad f, g, J and H at the same x; ipopt.py:41-53).
+extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, const double* sig, const int* modes,
+                           int n_modes, double* const* outs) {
+  if (!e || !x || !modes || !outs || n_modes < 1) return fail("pk_eval_set: bad argument");
+  CK(cudaSetDevice(e->device));
+  bool hess = false;
+  for (int k = 0; k < n_modes; ++k) {
+    if (modes[k] < 0 || modes[k] >= PK_N_MODES || !e->mode[modes[k]].loaded) return fail("pk_eval_set: mode not loaded");
+    if (!outs[k]) return fail("pk_eval_set: null output");
+    for (int q = 0; q < k; ++q)
+      if (modes[q] == modes[k]) return fail("pk_eval_set: a mode may appear only once");
+    hess = hess || modes[k] == PK_MODE_HESSIAN;
+  }
+  if (hess && (!lam || !sig)) return fail("pk_eval_set: multipliers required for the Hessian");
+  if (pk_upload_x(e, x)) return 1;
+  if (hess && pk_upload_multipliers(e, lam, sig)) return 1;
+  CK(cudaEventRecord(e->fork, e->stream));
+  // largest outputs first: their copies keep the copy engine busy while the small modes compute
+  std::vector<int> order(n_modes);
+  for (int k = 0; k < n_modes; ++k) order[k] = k;
+  for (int a = 1; a < n_modes; ++a)
+    for (int b = a; b > 0 && e->mode[modes[order[b]]].n_out > e->mode[modes[order[b - 1]]].n_out; --b) {
+      const int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t;
+    }
+  for (int q = 0; q < n_modes; ++q) {
+    const int k = order[q];
+    ModeState& ms = e->mode[modes[k]];
+    CK(cudaStreamWaitEvent(ms.stream, e->fork, 0));
+    if (launch_mode(e, modes[k], ~0u, ms.stream)) return 1;
+    if (download_async(e, modes[k], outs[k], ms.stream)) return 1;
+    CK(cudaEventRecord(ms.done, ms.stream));
+    CK(cudaStreamWaitEvent(e->stream, ms.done, 0));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
 }
 
 extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float* ms_stage) {

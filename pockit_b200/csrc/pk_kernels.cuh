@@ -374,6 +374,32 @@ __global__ void __launch_bounds__(PK_THREADS) pk_grad_scalar(PkCtx cx, const pk_
   cx.OUT[(long long)b * cx.n_out + jb.i[0]] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// de-duplicated pattern (opt-in): the reference's COO patterns repeat a (row, col) pair once per
+// contributing list entry and leave the summation to the consumer (Ipopt triplets, scipy.py:13-29).
+// With compaction enabled the engine sums the duplicates itself -- OUTC[u] = sum of OUT[perm[j]] for
+// j in [ptr[u], ptr[u+1]), in increasing slot order (the order a consumer walking the triplets would
+// use) -- so only the unique entries cross PCIe.  The values were written a moment ago and are
+// still L2-resident; one thread per unique entry, loads pipelined four deep.
+__global__ void __launch_bounds__(PK_THREADS) pk_compact(const double* __restrict__ OUT, double* __restrict__ OUTC,
+                                                        const unsigned* __restrict__ ptr, const unsigned* __restrict__ perm,
+                                                        long long n_out, long long n_unique, int B) {
+  const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
+  if (gid >= n_unique * B) return;
+  const int b = (int)(gid / n_unique);
+  const long long u = gid - (long long)b * n_unique;
+  const double* src = OUT + (long long)b * n_out;
+  unsigned j = ptr[u];
+  const unsigned hi = ptr[u + 1];
+  double acc = 0.0;
+  for (; j + 4 <= hi; j += 4) {
+    const double v0 = src[perm[j]], v1 = src[perm[j + 1]], v2 = src[perm[j + 2]], v3 = src[perm[j + 3]];
+    acc += v0; acc += v1; acc += v2; acc += v3;
+  }
+  for (; j < hi; ++j) acc += src[perm[j]];
+  OUTC[(long long)b * n_unique + u] = acc;
+}
+
 // L2 flush helper for timing hygiene
 __global__ void pk_fill(double* p, long long n, double v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;

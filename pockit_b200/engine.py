@@ -80,6 +80,10 @@ def load_library():
         "pk_eval_constraints": ([vp, vp, vp], C.c_int),
         "pk_eval_jacobian": ([vp, vp, vp], C.c_int),
         "pk_eval_hessian": ([vp, vp, vp, vp, vp], C.c_int),
+        "pk_eval_set": ([vp, vp, vp, vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)], C.c_int),
+        "pk_engine_set_output_runs": ([vp, C.c_int, vp, C.c_int64], C.c_int),
+        "pk_engine_set_compaction": ([vp, C.c_int, C.c_int64, vp, vp], C.c_int),
+        "pk_out_size": ([vp, C.c_int, C.POINTER(C.c_int64)], C.c_int),
         "pk_upload_x": ([vp, vp], C.c_int),
         "pk_upload_multipliers": ([vp, vp, vp], C.c_int),
         "pk_run": ([vp, C.c_int], C.c_int),
@@ -137,7 +141,9 @@ class Engine:
         for m in range(N_MODES):
             self.fin[m] = self.plan.finalize(m)
         lo = lowering
-        self.n_out = {m: self.fin[m]["n_out"] for m in range(N_MODES)}
+        self.n_out = {m: self.fin[m]["n_out"] for m in range(N_MODES)}  # slots on the device
+        self.n_host = dict(self.n_out)  # values the host receives (smaller with a de-duplicated pattern)
+        self.compacted = set()  # modes whose duplicates are summed on the device
         dims = _Dims(
             1, self.B, lo.r_s, lo.m, lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c,
             max(1, max(f["n_scalar"] for f in self.fin.values())),
@@ -225,7 +231,7 @@ class Engine:
         return x
 
     def _out(self, mode: int, out: Optional[np.ndarray]) -> np.ndarray:
-        n = self.B * self.n_out[mode]
+        n = self.B * self.n_host[mode]
         if out is None:
             if self.reuse_outputs:
                 # page-locked, engine-owned result buffers: D2H at full PCIe rate, no per-call
@@ -239,7 +245,64 @@ class Engine:
         return out
 
     def _shape(self, mode, out):
-        return out if self.B == 1 else out.reshape(self.B, self.n_out[mode])
+        return out if self.B == 1 else out.reshape(self.B, self.n_host[mode])
+
+    # ------------------------------------------------------------------ output shaping
+    def set_compaction(self, mode: int, seg_ptr: Optional[np.ndarray], perm: Optional[np.ndarray]):
+        """De-duplicated pattern for ``mode``: unique entry ``u`` is the sum of the slots
+        ``perm[seg_ptr[u]:seg_ptr[u+1]]``; ``None`` restores the reference pattern."""
+        self.load(mode)
+        if seg_ptr is None:
+            self._check(self.lib.pk_engine_set_compaction(self._h, mode, 0, None, None))
+            self.n_host[mode] = self.n_out[mode]
+            self.compacted.discard(mode)
+        else:
+            seg_ptr = np.ascontiguousarray(seg_ptr, dtype=np.int64)
+            perm = np.ascontiguousarray(perm, dtype=np.int64)
+            if len(perm) != self.n_out[mode]:
+                raise ValueError("perm must list every slot of the mode once")
+            self._check(self.lib.pk_engine_set_compaction(self._h, mode, len(seg_ptr) - 1, _ptr(seg_ptr), _ptr(perm)))
+            self.n_host[mode] = len(seg_ptr) - 1
+            self.compacted.add(mode)
+        self._pinned.pop(mode, None)
+
+    def set_output_runs(self, mode: int, runs: Optional[np.ndarray]):
+        """Mesh shard: ``runs`` = ``[(offset, count), ...]`` of the output this engine computes and
+        copies back (``None``: everything)."""
+        self.load(mode)
+        if runs is None or len(runs) == 0:
+            self._check(self.lib.pk_engine_set_output_runs(self._h, mode, None, 0))
+        else:
+            runs = np.ascontiguousarray(runs, dtype=np.int64).reshape(-1, 2)
+            self._check(self.lib.pk_engine_set_output_runs(self._h, mode, _ptr(runs), len(runs)))
+
+    def evaluate(self, x, fct_c=None, fct_o=None, modes=None, outs=None):
+        """Several callbacks at one ``x`` in a single engine call (``pk_eval_set``): ``x`` and the
+        multipliers are uploaded once, the modes run concurrently and each result is copied back as
+        soon as it is ready.  Returns ``{mode: array}``; the Hessian is included when ``fct_c`` is given."""
+        if modes is None:
+            modes = [P.OBJ, P.GRAD, P.CONS, P.JAC] + ([P.HESS] if fct_c is not None else [])
+        modes = list(modes)
+        for m in modes:
+            self.load(m)
+        x = self._x(x)
+        lam = sig = None
+        if P.HESS in modes:
+            if fct_c is None:
+                raise ValueError("the Hessian needs the multipliers fct_c (and fct_o)")
+            lam = np.ascontiguousarray(fct_c, dtype=np.float64)
+            if lam.size != self.B * self.lowering.m:
+                raise ValueError(f"fct_c must have {self.B * self.lowering.m} entries")
+            sig = np.ascontiguousarray(np.broadcast_to(np.asarray(1.0 if fct_o is None else fct_o, dtype=np.float64), (self.B,)))
+        bufs = [self._out(m, None if outs is None else outs[k]) for k, m in enumerate(modes)]
+        marr = (C.c_int * len(modes))(*modes)
+        parr = (C.c_void_p * len(modes))(*[b.ctypes.data for b in bufs])
+        self._check(self.lib.pk_eval_set(self._h, _ptr(x), None if lam is None else _ptr(lam),
+                                         None if sig is None else _ptr(sig), marr, len(modes), parr))
+        res = {}
+        for m, b in zip(modes, bufs):
+            res[m] = (np.float64(b[0]) if self.B == 1 else b) if m == P.OBJ else self._shape(m, b)
+        return res
 
     def objective(self, x):
         self.load(P.OBJ)
@@ -276,14 +339,16 @@ class Engine:
         return self._shape(P.HESS, out)
 
     def hessian_o(self, x):
-        n_o = self.lowering.nnz_hess_o
         full = self.hessian(x, self._zero_lam[: self.B * self.lowering.m], self._one)
-        return np.array(full[..., :n_o])
+        if P.HESS in self.compacted:  # de-duplicated: both parts live on the merged pattern
+            return np.array(full)
+        return np.array(full[..., : self.lowering.nnz_hess_o])
 
     def hessian_c(self, x, fct_c):
-        n_o = self.lowering.nnz_hess_o
         full = self.hessian(x, fct_c, np.zeros(self.B))
-        return np.array(full[..., n_o:])
+        if P.HESS in self.compacted:
+            return np.array(full)
+        return np.array(full[..., self.lowering.nnz_hess_o :])
 
     # ------------------------------------------------------------------ device-resident path
     def upload(self, x, fct_c=None, fct_o=None):
