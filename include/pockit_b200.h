@@ -176,6 +176,10 @@ int pk_flush_l2(pk_engine *e);                        /* overwrite a buffer larg
 /* pinned host memory for zero-copy NumPy views */
 void *pk_alloc_host(size_t bytes);
 void pk_free_host(void *p);
+/* page-lock / release a caller-owned range (a shared-memory mapping the ranks of a sharded mesh
+ * copy their shares into); needs a current CUDA device */
+int pk_host_register(void *p, size_t bytes);
+int pk_host_unregister(void *p);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,19 @@ extern "C" void pk_free_host(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+// Page-lock a caller-owned host range (e.g. a shared-memory mapping that several ranks copy
+// their shares of a result into) so device-to-host copies into it run at full PCIe rate.
+extern "C" int pk_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return fail("pk_host_register: bad argument");
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+extern "C" int pk_host_unregister(void* p) {
+  if (!p) return 0;
+  CK(cudaHostUnregister(p));
+  return 0;
+}
+
 extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   if (!d || !out) return fail("pk_engine_create: null argument");
   if (d->abi_version != PK_ABI_VERSION) return fail("pk_engine_create: ABI version mismatch");

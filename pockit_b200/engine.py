@@ -96,6 +96,8 @@ def load_library():
         "pk_flush_l2": ([vp], C.c_int),
         "pk_alloc_host": ([C.c_size_t], vp),
         "pk_free_host": ([vp], None),
+        "pk_host_register": ([vp, C.c_size_t], C.c_int),
+        "pk_host_unregister": ([vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)
@@ -130,11 +132,13 @@ class Engine:
     """One CUDA engine for one lowered system (``batch`` independent instances)."""
 
     def __init__(self, lowering, batch: int = 1, fastmath: bool = False, device: Optional[int] = None,
-                 fixed: Optional[np.ndarray] = None):
+                 fixed: Optional[np.ndarray] = None, shard: Optional[tuple] = None):
         self.lib = load_library()
         self.lowering = lowering
         self.B = int(batch)
-        self.plan = P.DevicePlan(lowering, self.B, fastmath, fused=os.environ.get("POCKIT_B200_FUSED", "0") == "1")
+        self.shard = shard
+        self.plan = P.DevicePlan(lowering, self.B, fastmath, shard=shard,
+                                 fused=shard is None and os.environ.get("POCKIT_B200_FUSED", "0") == "1")
         self.fin = {}
         for m in range(N_MODES):
             self.plan.mode(m)
@@ -222,6 +226,12 @@ class Engine:
             d.n_jobs[s] = len(arr)
         self._check(self.lib.pk_engine_load_mode(self._h, mode, C.byref(d)))
         self._loaded.add(mode)
+        runs = f.get("runs")
+        if runs is not None:  # mesh shard: copy back only what this rank computes
+            if len(runs) == 0:
+                raise RuntimeError(f"mode {P.MODES[mode]} is evaluated by rank 0 of the sharded mesh, not by rank {self.shard[0]}")
+            if not (len(runs) == 1 and runs[0][0] == 0 and runs[0][1] == f["n_out"]):
+                self._check(self.lib.pk_engine_set_output_runs(self._h, mode, _ptr(np.ascontiguousarray(runs)), len(runs)))
 
     # ------------------------------------------------------------------ host-to-host callbacks
     def _x(self, x) -> np.ndarray:

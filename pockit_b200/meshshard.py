@@ -1,0 +1,254 @@
+"""One fine mesh evaluated by several GPUs ("one very fine mesh").
+
+The callback values of a 40 k - 100 k node transcription are 200+ MB per evaluation set and
+the consumer (Ipopt / SciPy) lives on the host, so the path is bound by the device-to-host
+copy, not by the kernels.  Sharding therefore splits what is expensive -- the slot-streaming
+expansion and the copy -- and replicates what is cheap:
+
+* every rank (one process per GPU) receives the whole ``x`` (and multipliers; 2.9 + 1.9 MB for
+  robot_arm LGR 2000x20) and runs the per-node programs, the quadrature sums and the system
+  program for all nodes: a few microseconds, and it makes the integrals bit-identical on every
+  rank without an all-reduce -- the data path has **no collective**;
+* rank ``g`` runs the block expansion for the intervals ``[nK g / G, nK (g+1) / G)`` of every list
+  and its share of the long table / constant runs (``plan.ModePlan._shard``), and copies exactly
+  those slot runs over *its own* PCIe link into a host buffer shared by all ranks
+  (a ``/dev/shm`` mapping, page-locked in every process), at the offsets of the reference pattern;
+* rank 0 is the caller: it owns the small callbacks (objective, gradient, constraints), publishes
+  ``x`` in the shared mapping, evaluates its own share and waits for the others' completion flags.
+
+Values and patterns are exactly those of the unsharded engine (the same kernels write the same
+slots); only who writes which slot changes.  ``torch.distributed`` is used for the rendezvous
+(sharing the mapping's name) -- NCCL on the GPU box, gloo in the CPU tests.
+
+Usage (all ranks)::
+
+    ms = MeshShardedSystem(system)          # collective
+    if ms.rank == 0:
+        ... ms.jacobian(x) / ms.hessian(x, lam, sigma) / ms.evaluate(x, lam, sigma) ...
+        ms.close()                          # releases the workers
+    else:
+        ms.serve()                          # returns when rank 0 closes
+"""
+from __future__ import annotations
+
+import mmap
+import os
+import time
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import plan as P
+
+__all__ = ["MeshShardedSystem"]
+
+_CTRL = 64  # int64 control words: [0] sequence, [1] command, [8+g] done sequence of rank g, [24+g] error flag
+_CMD_JAC, _CMD_HESS, _CMD_EXIT = 1, 2, 4
+_PAGE = 4096
+
+
+def _round(n: int, to: int = _PAGE) -> int:
+    return (n + to - 1) // to * to
+
+
+class _SharedBuffers:
+    """The mapping all ranks see: control words, inputs, and the two large value arrays."""
+
+    def __init__(self, path: str, create: bool, L: int, m: int, nnz_j: int, nnz_h: int):
+        self.path = path
+        off = _round(8 * _CTRL)
+        self.off = {}
+        for name, n in (("x", L), ("lam", max(m, 1)), ("sig", 1), ("jac", max(nnz_j, 1)), ("hess", max(nnz_h, 1))):
+            self.off[name] = (off, n)
+            off = _round(off + 8 * n)
+        self.size = off
+        flags = os.O_RDWR | (os.O_CREAT | os.O_EXCL if create else 0)
+        fd = os.open(path, flags, 0o600)
+        try:
+            if create:
+                os.ftruncate(fd, self.size)
+            self.mm = mmap.mmap(fd, self.size, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        finally:
+            os.close(fd)
+        self.ctrl = np.frombuffer(self.mm, dtype=np.int64, count=_CTRL, offset=0)
+        self.arr = {k: np.frombuffer(self.mm, dtype=np.float64, count=n, offset=o) for k, (o, n) in self.off.items()}
+        self.address = np.frombuffer(self.mm, dtype=np.uint8).ctypes.data
+
+    def unlink(self):
+        try:
+            os.unlink(self.path)
+        except FileNotFoundError:
+            pass
+
+
+class MeshShardedSystem:
+    def __init__(self, system, rank: Optional[int] = None, world: Optional[int] = None, device: Optional[int] = None,
+                 make_engine: Optional[Callable] = None, page_lock: bool = True, shm_dir: str = "/dev/shm"):
+        self.system = system
+        self.rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
+        self.world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else int(world)
+        if self.world > 16:
+            raise ValueError("at most 16 ranks per sharded mesh")
+        lo = self.lowering = system.lowering
+        self.L, self.m = lo.r_s, lo.m
+        self.nnz_jac, self.nnz_hess = lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c
+        shard = (self.rank, self.world)
+        if make_engine is None:
+            from .engine import Engine  # raises without the CUDA library / a device
+
+            if device is None:
+                device = int(os.environ.get("LOCAL_RANK", str(self.rank)))
+            make_engine = lambda lowering, sh: Engine(lowering, fastmath=system._fastmath, device=device, shard=sh)  # noqa: E731
+        self.engine = make_engine(lo, shard)
+        # rendezvous: rank 0 creates the mapping, everybody attaches, then the name is removed
+        path = [f"{shm_dir}/pockit_b200_mesh_{os.getpid()}_{time.time_ns() & 0xFFFFFF:x}" if self.rank == 0 else None]
+        if self.rank == 0:
+            self.buf = _SharedBuffers(path[0], True, self.L, self.m, self.nnz_jac, self.nnz_hess)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                raise RuntimeError("MeshShardedSystem with world > 1 needs torch.distributed to be initialised")
+            dist.broadcast_object_list(path, src=0)
+            if self.rank != 0:
+                self.buf = _SharedBuffers(path[0], False, self.L, self.m, self.nnz_jac, self.nnz_hess)
+            dist.barrier()
+        if self.rank == 0:
+            self.buf.unlink()
+        self._locked = False
+        if page_lock and hasattr(self.engine, "lib"):
+            self.engine._check(self.engine.lib.pk_host_register(self.buf.address, self.buf.size))
+            self._locked = True
+        self._seq = int(self.buf.ctrl[0])
+        self.pinned_outputs = False
+        self._closed = False
+
+    # ------------------------------------------------------------------ structures (unchanged)
+    def jacobianstructure(self):
+        return self.system.jacobianstructure()
+
+    def hessianstructure(self):
+        return self.system.hessianstructure()
+
+    # ------------------------------------------------------------------ worker side
+    @staticmethod
+    def _wait(cond, what: str, timeout: float = 600.0):
+        t0 = time.perf_counter()
+        spins = 0
+        while not cond():
+            spins += 1
+            if spins > 20000:  # ~ a few ms of polling, then yield the core
+                time.sleep(0.0002)
+                if time.perf_counter() - t0 > timeout:
+                    raise TimeoutError(f"mesh shard: timed out waiting for {what}")
+
+    def _run_share(self, cmd: int, extra_modes=()):
+        a = self.buf.arr
+        modes, outs = list(extra_modes), [None] * len(extra_modes)
+        if cmd & _CMD_JAC:
+            modes.append(P.JAC)
+            outs.append(a["jac"][: self.nnz_jac])
+        if cmd & _CMD_HESS:
+            modes.append(P.HESS)
+            outs.append(a["hess"][: self.nnz_hess])
+        if not modes:
+            return {}
+        lam = a["lam"][: self.m] if cmd & _CMD_HESS else None
+        return self.engine.evaluate(a["x"], lam, a["sig"] if cmd & _CMD_HESS else None, modes=modes, outs=outs)
+
+    def serve(self):
+        """Ranks > 0: evaluate this rank's share whenever rank 0 publishes a new point."""
+        if self.rank == 0:
+            raise RuntimeError("rank 0 is the caller, not a worker")
+        ctrl = self.buf.ctrl
+        while True:
+            self._wait(lambda: int(ctrl[0]) != self._seq, "the next evaluation point", timeout=float("inf"))
+            self._seq = int(ctrl[0])
+            cmd = int(ctrl[1])
+            if cmd & _CMD_EXIT:
+                break
+            try:
+                self._run_share(cmd)
+            except Exception:
+                ctrl[24 + self.rank] = 1
+                ctrl[8 + self.rank] = self._seq
+                raise
+            ctrl[8 + self.rank] = self._seq
+        self._release()
+
+    # ------------------------------------------------------------------ caller side (rank 0)
+    def _evaluate(self, cmd: int, x, fct_c=None, fct_o=None, extra_modes=()):
+        if self.rank != 0:
+            raise RuntimeError("only rank 0 calls the callbacks; the other ranks serve()")
+        a, ctrl = self.buf.arr, self.buf.ctrl
+        x = np.asarray(x, dtype=np.float64)
+        if x.size != self.L:
+            raise ValueError(f"x must have {self.L} entries")
+        a["x"][:] = x.reshape(-1)
+        if cmd & _CMD_HESS:
+            lam = np.asarray(fct_c, dtype=np.float64)
+            if lam.size != self.m:
+                raise ValueError(f"fct_c must have {self.m} entries")
+            a["lam"][: self.m] = lam.reshape(-1)
+            a["sig"][0] = float(fct_o)
+        ctrl[1] = cmd
+        self._seq += 1
+        ctrl[0] = self._seq  # publish (x86: stores are not reordered with earlier stores)
+        res = self._run_share(cmd, extra_modes)
+        for g in range(1, self.world):
+            self._wait(lambda g=g: int(ctrl[8 + g]) == self._seq, f"rank {g}")
+            if ctrl[24 + g]:
+                raise RuntimeError(f"mesh shard: rank {g} failed")
+        return res
+
+    def _view(self, name: str, n: int):
+        v = self.buf.arr[name][:n]
+        return v if self.pinned_outputs else v.copy()
+
+    def objective(self, x):
+        return self.engine.objective(x)
+
+    def gradient(self, x):
+        return self.engine.gradient(x)
+
+    def constraints(self, x):
+        return self.engine.constraints(x)
+
+    def jacobian(self, x):
+        self._evaluate(_CMD_JAC, x)
+        return self._view("jac", self.nnz_jac)
+
+    def hessian(self, x, fct_c, fct_o):
+        self._evaluate(_CMD_HESS, x, fct_c, fct_o)
+        return self._view("hess", self.nnz_hess)
+
+    def evaluate(self, x, fct_c=None, fct_o=1.0):
+        """The whole set at one ``x`` (see ``System.evaluate``), Jacobian / Hessian values sharded."""
+        cmd = _CMD_JAC | (_CMD_HESS if fct_c is not None else 0)
+        res = self._evaluate(cmd, x, fct_c, fct_o, extra_modes=(P.OBJ, P.GRAD, P.CONS))
+        out = {"objective": res[P.OBJ], "gradient": res[P.GRAD], "constraints": res[P.CONS],
+               "jacobian": self._view("jac", self.nnz_jac)}
+        if fct_c is not None:
+            out["hessian"] = self._view("hess", self.nnz_hess)
+        return out
+
+    # ------------------------------------------------------------------
+    def _release(self):
+        if self._closed:
+            return
+        self._closed = True
+        if self._locked:
+            try:
+                self.engine.lib.pk_host_unregister(self.buf.address)
+            except Exception:
+                pass
+        if hasattr(self.engine, "close"):
+            self.engine.close()
+
+    def close(self):
+        """Rank 0: release the workers and the engine."""
+        if self.rank == 0 and not self._closed:
+            self.buf.ctrl[1] = _CMD_EXIT
+            self._seq += 1
+            self.buf.ctrl[0] = self._seq
+        self._release()

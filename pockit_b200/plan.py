@@ -40,6 +40,7 @@ F_A_SCALAR, F_B_SCALAR, F_A_UNIT, F_B_UNIT, F_LAM = 1, 2, 4, 8, 16
 JOB_DTYPE = np.dtype([("type", "<i4"), ("flags", "<i4"), ("i", "<i8", (16,)), ("f", "<f8", (2,))])
 
 NODE_BLOCK = 128
+SPLIT_MIN = 1024  # slot runs shorter than this are not split between mesh shards (rank 0 owns them)
 
 
 class Pools:
@@ -127,7 +128,10 @@ class ModePlan:
         self.n_out = 0
         self.src = None
         self.expand_groups: dict = {}
+        self.owned_runs: Optional[list] = None  # mesh shard: (offset, count) runs of the output computed here
         self._build()
+        if owner.shard is not None:
+            self._shard(*owner.shard)
 
     # ---------------------------------------------------------------- allocation helpers
     def tab(self, value) -> int:
@@ -196,6 +200,99 @@ class ModePlan:
                 rec["i"][idx] = int(v)
         self.jobs[stage].append(rec)
         return rec
+
+    # ---------------------------------------------------------------- mesh sharding
+    def _shard(self, g: int, G: int):
+        """Keep only rank ``g``'s share of the slot-streaming work ("one very fine mesh").
+
+        The cheap, latency-bound part -- per-node programs, quadrature sums, system program -- is
+        *replicated* on every rank (a few microseconds on 40 k threads, and it makes the integrals
+        bit-identical everywhere without an all-reduce); the HBM- and PCIe-bound part is split:
+        every block expansion keeps a contiguous range of intervals, long table / constant /
+        scaled runs keep a contiguous sub-range, short runs and the small callbacks
+        (objective, gradient, constraints) stay on rank 0.  ``owned_runs`` lists the output
+        slots this rank produces; over all ranks they partition ``[0, n_out)``."""
+        lo = self.owner.lo
+        if self.mode not in (JAC, HESS):
+            self.owned_runs = [(0, self.n_out)] if g == 0 else []
+            if g != 0:
+                self.jobs = {s: [] for s in range(6)}
+            return
+
+        def part(count):
+            return count * g // G, count * (g + 1) // G
+
+        def clone(rec):
+            r = dict(rec)
+            r["i"] = list(rec["i"])
+            r["f"] = list(rec["f"])
+            r["rows"] = dict(rec["rows"])
+            return r
+
+        runs = []
+        generic = []
+        for rec in self.jobs[ST_GENERIC]:
+            t, dst, cnt = rec["type"], rec["i"][0], rec["i"][1]
+            splittable = cnt >= SPLIT_MIN and (
+                t in (J_CONST, J_EXPAND_TABLE) or (t == J_SCALED and not rec["flags"] & F_A_SCALAR)
+            )
+            if not splittable:
+                if g == 0:
+                    generic.append(rec)
+                    runs.append((dst, cnt))
+                continue
+            e0, e1 = part(cnt)
+            if e1 == e0:
+                continue
+            r = clone(rec)
+            r["i"][0], r["i"][1] = dst + e0, e1 - e0
+            if t == J_CONST:
+                r["i"][6] += e0
+            elif t == J_EXPAND_TABLE:
+                for k in (6, 7, 8):
+                    r["i"][k] += e0
+            else:
+                r["i"][8] += e0
+            generic.append(r)
+            runs.append((dst + e0, e1 - e0))
+        self.jobs[ST_GENERIC] = generic
+        expand = []
+        for rec in self.jobs[ST_EXPAND]:
+            n, rows = rec["i"][3], rec["i"][4]
+            Ka, Kb = part(rec["i"][11] // n)
+            if Kb == Ka:
+                continue
+            r = clone(rec)
+            r["i"][11] = (Kb - Ka) * n
+            r["i"][6] += Ka * rec["i"][5]
+            r["i"][8] += Ka
+            if rec["i"][2] >= 0:
+                r["i"][2] += Ka * rows
+            r["lists"] = [(dst + Ka * n * rows, row) for dst, row in rec["lists"]]
+            runs += [(dst, (Kb - Ka) * n * rows) for dst, _ in r["lists"]]
+            expand.append(r)
+        self.jobs[ST_EXPAND] = expand
+        # runs the (replicated) per-node programs write themselves: split ownership of the copy only
+        for pi, prog in enumerate(self.prog):
+            col = lo.phases[pi].col
+            for nset, _code, dst, _lam, _c_lo in prog.direct:
+                cnt = {"all": col.L_m, "mid": lo.low[pi].n_mid}.get(nset, 1)
+                if cnt >= SPLIT_MIN:
+                    e0, e1 = part(cnt)
+                    if e1 > e0:
+                        runs.append((dst + e0, e1 - e0))
+                elif g == 0:
+                    runs.append((dst, cnt))
+        runs.sort()
+        merged = []
+        for off, cnt in runs:
+            if cnt <= 0:
+                continue
+            if merged and merged[-1][0] + merged[-1][1] == off:
+                merged[-1] = (merged[-1][0], merged[-1][1] + cnt)
+            else:
+                merged.append((off, cnt))
+        self.owned_runs = merged
 
     # ---------------------------------------------------------------- build per mode
     def _build(self):
@@ -448,10 +545,19 @@ class ModePlan:
 class DevicePlan:
     """Pools + per-mode plans for one lowered system."""
 
-    def __init__(self, lo: SystemLowering, batch: int = 1, fastmath: bool = False, fused: bool = False):
+    def __init__(self, lo: SystemLowering, batch: int = 1, fastmath: bool = False, fused: bool = False,
+                 shard: Optional[tuple] = None):
         self.lo = lo
         self.B = int(batch)
         self.fastmath = fastmath
+        if shard is not None:
+            g, G = int(shard[0]), int(shard[1])
+            if not 0 <= g < G:
+                raise ValueError("shard must be (rank, world) with 0 <= rank < world")
+            if fused:
+                raise ValueError("mesh sharding is not available with the fused expansion variant")
+            shard = (g, G)
+        self.shard = shard
         # fused=True: the per-node program itself walks its block column and writes the slots (no
         # node-table round trip, one launch less).  Measured on B200 (round 1) it is SLOWER than the
         # node program + persistent pk_expand_blocks pair (robot_arm Hessian 40 us vs 31 us, humanoid
@@ -654,7 +760,7 @@ class DevicePlan:
         return dict(
             source=src, kernels=kernels, sys_kernel=sys_name, table=np.array(mp.table, dtype=np.int64),
             table_symbol=f"pk_tab_{MODES[m]}", jobs=jobs, n_scalar=mp.n_scalar, n_out=mp.n_out,
-            n_table=mp.n_table,
+            n_table=mp.n_table, runs=None if mp.owned_runs is None else np.array(mp.owned_runs, dtype=np.int64).reshape(-1, 2),
         )
 
     def _node_kernel(self, mp: ModePlan, pi: int, kname: str) -> str:

@@ -67,9 +67,9 @@ def _ptr(a):
 
 
 class HostEmu:
-    def __init__(self, system, batch=1, fixed=None, fused=False):
+    def __init__(self, system, batch=1, fixed=None, fused=False, shard=None):
         self.lo = system.lowering
-        self.dp = P.DevicePlan(self.lo, batch, fused=fused)
+        self.dp = P.DevicePlan(self.lo, batch, fused=fused, shard=shard)
         self.B = batch
         for m in range(5):
             self.dp.mode(m)

@@ -1,0 +1,68 @@
+"""CPU tier: mesh sharding of ONE fine mesh over several ranks.  Every rank's plan
+keeps a share of the slot-streaming jobs; emulated on the host, the shares must partition the
+output and reassemble, bit for bit, to the unsharded evaluation (and hence to the reference)."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, build, load
+from hostemu import HostEmu
+from pockit_b200 import plan as P
+
+
+def _assemble(S, G, mode, x, lam=None, sigma=None):
+    full = None
+    cover = None
+    for g in range(G):
+        E = HostEmu(S, shard=(g, G))
+        out = E.run(mode, x, lam, sigma)
+        runs = E.fin[mode]["runs"]
+        if full is None:
+            full = np.full(len(out), np.nan)
+            cover = np.zeros(len(out), dtype=np.int64)
+        for off, cnt in runs:
+            full[off : off + cnt] = out[off : off + cnt]
+            cover[off : off + cnt] += 1
+    return full, cover
+
+
+@pytest.mark.parametrize("split_min", [4, 1024])
+@pytest.mark.parametrize("G", [2, 3, 8])
+@pytest.mark.parametrize("case", ["robot_arm_lgr_6x20", "rocket_lgl_4x5", "quadrotor_lgl_14x6", "general_lgl", "general_lgr", "tiny_lgl_2x2"])
+def test_shards_partition_and_reassemble(case, G, split_min, monkeypatch):
+    monkeypatch.setattr(P, "SPLIT_MIN", split_min)
+    S, g = build(case), load(case)
+    x, lam, sigma = g["x"], g["lam"], float(g["sigma"])
+    whole = HostEmu(S)
+    for mode, args, name in ((P.JAC, (x,), "jacobian"), (P.HESS, (x, lam, sigma), "hessian"),
+                             (P.CONS, (x,), "constraints"), (P.GRAD, (x,), "gradient"), (P.OBJ, (x,), "objective")):
+        full, cover = _assemble(S, G, mode, *args)
+        assert np.all(cover == 1), f"{name}: every slot must be owned by exactly one rank"
+        assert np.array_equal(full, whole.run(mode, *args)), name
+        assert_close(full if mode != P.OBJ else full[0], g[name], name)
+
+
+def test_fine_mesh_shares_are_balanced():
+    import pockit_b200.radau as rad
+    from pockit_b200 import problems
+
+    S = problems.robot_arm(rad, mesh=400, num_point=20)
+    lo = S.lowering
+    G = 8
+    for mode, n_out in ((P.JAC, lo.nnz_jac), (P.HESS, lo.nnz_hess_o + lo.nnz_hess_c)):
+        owned = []
+        for g in range(G):
+            dp = P.DevicePlan(lo, shard=(g, G))
+            for m in range(5):
+                dp.mode(m)
+            runs = dp.finalize(mode)["runs"]
+            owned.append(int(runs[:, 1].sum()))
+        assert sum(owned) == n_out
+        assert max(owned) <= 1.1 * n_out / G  # near-equal shares: the copy time is what shards
+
+
+def test_bad_shard_arguments():
+    S = build("tiny_lgl_2x2")
+    with pytest.raises(ValueError):
+        P.DevicePlan(S.lowering, shard=(2, 2))
+    with pytest.raises(ValueError):
+        P.DevicePlan(S.lowering, shard=(0, 2), fused=True)

@@ -88,3 +88,77 @@ def test_two_rank_sharded_batch_matches_unsharded():
         p.join(timeout=300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+# ---------------------------------------------------------------------------------------------
+# one fine mesh split over two ranks (pockit_b200.meshshard): shared host buffer, no collective
+def _mesh_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    import pockit_b200.radau as rad
+    from hostemu import HostEmu
+    from pockit_b200 import plan as P
+    from pockit_b200 import problems
+    from pockit_b200.meshshard import MeshShardedSystem
+
+    P.SPLIT_MIN = 16  # let the small test problem split its table / constant runs too
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    S = problems.robot_arm(rad, mesh=12, num_point=5)
+
+    class EmuEngine:  # CPU stand-in for Engine(shard=...) (test infrastructure)
+        def __init__(self, lowering, shard):
+            self.e = HostEmu(S, shard=shard)
+
+        def evaluate(self, x, fct_c=None, fct_o=None, modes=None, outs=None):
+            res = {}
+            for k, m in enumerate(modes):
+                full = self.e.run(m, x, fct_c, None if fct_o is None else float(np.asarray(fct_o).reshape(-1)[0]))
+                out = outs[k] if outs is not None and outs[k] is not None else np.full(len(full), np.nan)
+                for off, cnt in self.e.fin[m]["runs"]:
+                    out[off : off + cnt] = full[off : off + cnt]
+                res[m] = out[0] if m == P.OBJ else out
+            return res
+
+        def objective(self, x):
+            return self.e.run(P.OBJ, x)[0]
+
+    ms = MeshShardedSystem(S, make_engine=EmuEngine)
+    if rank != 0:
+        ms.serve()
+    else:
+        whole = HostEmu(S)
+        ok = True
+        for seed in (3, 4):
+            x, lam, sigma = problems.evaluation_point(S, seed=seed)
+            ok &= np.array_equal(ms.jacobian(x), whole.run(P.JAC, x))
+            ok &= np.array_equal(ms.hessian(x, lam, 0.5), whole.run(P.HESS, x, lam, 0.5))
+            r = ms.evaluate(x, lam, sigma)
+            ok &= np.array_equal(r["jacobian"], whole.run(P.JAC, x))
+            ok &= np.array_equal(r["hessian"], whole.run(P.HESS, x, lam, sigma))
+            ok &= np.array_equal(r["constraints"], whole.run(P.CONS, x))
+            ok &= np.array_equal(r["gradient"], whole.run(P.GRAD, x))
+            ok &= r["objective"] == whole.run(P.OBJ, x)[0]
+        # both ranks really contributed: rank 1 owns part of the Jacobian
+        ok &= len(HostEmu(S, shard=(1, 2)).fin[P.JAC]["runs"]) > 0
+        q.put(bool(ok))
+        ms.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_mesh_shard_matches_unsharded():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mesh_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
