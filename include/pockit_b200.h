@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PK_ABI_VERSION 1
+#define PK_ABI_VERSION 2
 
 typedef struct pk_engine pk_engine;
 
@@ -37,7 +37,13 @@ enum {
   PK_MODE_GRADIENT = 2,    /* SystemBase.gradient    systembase.py:646 */
   PK_MODE_JACOBIAN = 3,    /* SystemBase.jacobian    systembase.py:676 */
   PK_MODE_HESSIAN = 4,     /* SystemBase.hessian     systembase.py:820 (hessian_o :735, hessian_c :786) */
-  PK_N_MODES = 5
+  PK_N_CALLBACKS = 5,
+  /* all five callbacks at one (x, lambda, sigma) as ONE pipeline: a single per-node program evaluates
+   * every leaf once, one reduction and one system program feed all consumers; outputs in one buffer
+   * [objective | gradient | constraints | Jacobian values | Hessian values].  Used by pk_run_set /
+   * pk_eval_set / pk_time_steps when all five callbacks are requested and this mode is loaded. */
+  PK_MODE_SET = 5,
+  PK_N_MODES = 6
 };
 
 /* job stages (which hand-written kernel consumes the record) */
@@ -106,6 +112,9 @@ typedef struct {
   int64_t n_out;                     /* outputs per instance */
   const pk_job *jobs[PK_N_STAGES];
   int64_t n_jobs[PK_N_STAGES];
+  int64_t grad_offset, grad_count;     /* output slots the gradient gather-sums into (zeroed first); count 0: none */
+  int64_t sub_offset[PK_N_CALLBACKS];  /* PK_MODE_SET: where each callback's values start in the combined output */
+  int64_t sub_count[PK_N_CALLBACKS];   /* ... and how many there are (0 for the single-callback modes) */
 } pk_mode_desc;
 
 int pk_abi_version(void);
@@ -170,6 +179,10 @@ int pk_time(pk_engine *e, int mode, int iters, float *ms_total, float *ms_stage 
 /* device-resident throughput: `steps` times { [flush L2, untimed]; event; pk_run_set(modes); event };
  * ms_steps[s] is the CUDA-event time of step s on the engine stream */
 int pk_time_steps(pk_engine *e, const int *modes, int n_modes, int steps, int flush_l2, float *ms_steps);
+/* device-side timeline of one evaluation set (per-mode streams, timing events around every launch):
+ * rows[4*i..] = (mode, tag, edge, microseconds); tag = job stage 0..5, 6 node programs, 7 system
+ * program, 8 compaction; edge 0 = before, 1 = after; the last row (mode -1) is the whole set */
+int pk_timeline(pk_engine *e, const int *modes, int n_modes, double *rows, int max_rows, int *n_rows);
 int pk_kernel_launches(pk_engine *e, int64_t *count); /* kernels launched so far by this engine */
 int pk_flush_l2(pk_engine *e);                        /* overwrite a buffer larger than L2 */
 

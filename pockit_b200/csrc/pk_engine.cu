@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "pk_kernels.cuh"
@@ -31,6 +32,16 @@ static int fail(const std::string& msg) {
                   std::to_string(__LINE__) + ")");                                                 \
   } while (0)
 
+// one launch of the block expansion: jobs [first, first + count) of the mode's EXPAND stage
+struct ExpandGroup {
+  long long first = 0, count = 0;
+  bool lam = false;
+  // persistent column kernel (any mix of orders)
+  long long* prefix = nullptr; long long blocks = 0; int uniform = 0; size_t smem = 0;
+  // parameter-driven column kernel (same-order meshes, few jobs / lists)
+  bool cols = false; PkXcParams xc; unsigned xc_gx = 0; size_t xc_smem = 0;
+};
+
 struct ModeState {
   bool loaded = false;
   cudaLibrary_t lib = nullptr;
@@ -49,13 +60,15 @@ struct ModeState {
   long long n_jobs[PK_N_STAGES] = {};
   // block -> (job, chunk) maps of the two slot-streaming kernels
   int* gen_job = nullptr; int* gen_chunk = nullptr; long long gen_blocks = 0;
-  long long* exp_prefix = nullptr; long long exp_blocks = 0; int exp_uniform = 0;
-  size_t exp_smem = 0;
+  std::vector<ExpandGroup> exp;  // block expansion, one launch per group
   long long max_defect_rows = 0, max_grad_count = 0, max_reduce_len = 0;
   size_t def_smem = 0;
   double* red_partial = nullptr; unsigned* red_ticket = nullptr; int red_parts = 0;
   bool def_fast = false, def_table = false;
   bool idx32 = true;  // every flattened (instance, slot) space fits 32-bit index math
+  long long grad_off = 0, grad_cnt = 0;
+  long long sub_off[PK_N_CALLBACKS] = {}, sub_cnt[PK_N_CALLBACKS] = {};
+  bool in_set = false;  // callback mode: the latest values live in the set pipeline's combined output
   // mesh sharding: the (offset, count) runs of the output this engine computes; empty = all of it
   std::vector<long long> dl_runs;
   // de-duplicated pattern: OUTC[u] = sum of OUT[perm[ptr[u] .. ptr[u+1])]
@@ -73,12 +86,30 @@ struct pk_engine {
   cudaGraphExec_t set_graph = nullptr;  // captured evaluation set (all requested modes, one stream each)
   std::vector<int> set_modes;
   double* dpool = nullptr; long long* ipool = nullptr;
-  double *hX = nullptr, *hLAM = nullptr, *hSIG = nullptr, *hOUT = nullptr;  // pinned staging
+  std::vector<long long> h_ipool;  // host copy (list tables are folded into kernel parameters)
+  double *hX = nullptr, *hLAM = nullptr, *hSIG = nullptr;  // pinned staging
   double* flush = nullptr; long long n_flush = 0;
   long long n_out_max = 0;
   ModeState mode[PK_N_MODES];
   long long launches = 0, set_launches = 0;
+  // pk_timeline: timing events around every launch of a set
+  struct Mark { cudaEvent_t ev; int mode, tag, edge; };
+  std::vector<Mark>* trace = nullptr;
+  // set launches: the HBM-bound block expansions of different modes are chained one after the other
+  // (each then streams at full bandwidth while the next mode's latency-bound prologue overlaps it)
+  cudaEvent_t chain_ev[PK_N_MODES] = {};
+  int chain_last = -1;
+  bool chain = false;
 };
+
+// tag: job stage 0..5, 6 node programs, 7 system program, 8 compaction; edge 0 = before, 1 = after
+static void tr(pk_engine* e, int mode, int tag, int edge, cudaStream_t s) {
+  if (!e->trace) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, s);
+  e->trace->push_back({ev, mode, tag, edge});
+}
 
 extern "C" int pk_abi_version(void) { return PK_ABI_VERSION; }
 extern "C" const char* pk_last_error(void) { return g_err.c_str(); }
@@ -127,7 +158,7 @@ extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   if (d->nnz_jac > n_out) n_out = d->nnz_jac;
   if (d->nnz_hess > n_out) n_out = d->nnz_hess;
   if (n_out < 1) n_out = 1;
-  e->n_out_max = n_out;
+  e->n_out_max = 1 + d->L + d->m + d->nnz_jac + d->nnz_hess;  // the set pipeline holds all five
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   auto dev = [&](double** p, long long count) { return cudaMalloc((void**)p, sizeof(double) * (size_t)(count > 0 ? count : 1)); };
   CK(dev(&e->X, B * d->L));
@@ -139,10 +170,10 @@ extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   CK(cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->x_done, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->lam_done, cudaEventDisableTiming));
+  for (auto& ev : e->chain_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&e->hX, sizeof(double) * (size_t)(B * d->L > 0 ? B * d->L : 1)));
   CK(cudaMallocHost((void**)&e->hLAM, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1)));
   CK(cudaMallocHost((void**)&e->hSIG, sizeof(double) * (size_t)B));
-  CK(cudaMallocHost((void**)&e->hOUT, sizeof(double) * (size_t)(B * n_out)));
   CK(cudaStreamSynchronize(e->stream));
   *out = e;
   return 0;
@@ -155,7 +186,8 @@ static void free_mode(ModeState& ms) {
   }
   if (ms.gen_job) cudaFree(ms.gen_job);
   if (ms.gen_chunk) cudaFree(ms.gen_chunk);
-  if (ms.exp_prefix) cudaFree(ms.exp_prefix);
+  for (auto& g : ms.exp)
+    if (g.prefix) cudaFree(g.prefix);
   if (ms.lib) cudaLibraryUnload(ms.lib);
   if (ms.OUT) cudaFree(ms.OUT);
   if (ms.S) cudaFree(ms.S);
@@ -183,8 +215,10 @@ extern "C" int pk_engine_destroy(pk_engine* e) {
   if (e->fork) cudaEventDestroy(e->fork);
   if (e->x_done) cudaEventDestroy(e->x_done);
   if (e->lam_done) cudaEventDestroy(e->lam_done);
+  for (auto& ev : e->chain_ev)
+    if (ev) cudaEventDestroy(ev);
   cudaFree(e->FIX); cudaFree(e->dpool); cudaFree(e->ipool); cudaFree(e->flush);
-  cudaFreeHost(e->hX); cudaFreeHost(e->hLAM); cudaFreeHost(e->hSIG); cudaFreeHost(e->hOUT);
+  cudaFreeHost(e->hX); cudaFreeHost(e->hLAM); cudaFreeHost(e->hSIG);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return 0;
@@ -199,6 +233,7 @@ extern "C" int pk_engine_set_pools(pk_engine* e, const double* dp, int64_t nd, c
   CK(cudaMalloc((void**)&e->ipool, sizeof(long long) * (size_t)(ni > 0 ? ni : 1)));
   if (nd > 0) CK(cudaMemcpy(e->dpool, dp, sizeof(double) * (size_t)nd, cudaMemcpyHostToDevice));
   if (ni > 0) CK(cudaMemcpy(e->ipool, ip, sizeof(long long) * (size_t)ni, cudaMemcpyHostToDevice));
+  e->h_ipool.assign(ip, ip + (ni > 0 ? ni : 0));
   return 0;
 }
 
@@ -264,6 +299,77 @@ static int build_block_map(const pk_job* jobs, long long n, int field, int per, 
   return 0;
 }
 
+static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, long long count, ExpandGroup& g) {
+  g.first = first;
+  g.count = count;
+  g.lam = (ej[0].flags & PK_F_LAM) != 0;
+  std::vector<long long> prefix(1, 0);
+  g.uniform = 1;
+  long long n_lists = 0, max_pairs = 0;
+  for (long long j = 0; j < count; ++j) {
+    const pk_job& jb = ej[j];
+    if (jb.i[11] >= (1LL << 31) || jb.i[1] * jb.i[11] >= (1LL << 32)) return fail("expand job too large for 32-bit unit indices");
+    prefix.push_back(prefix.back() + jb.i[1] * jb.i[11]);
+    const size_t sm = sizeof(double) * (size_t)(jb.i[3] * jb.i[4]);
+    if (sm > g.smem) g.smem = sm;
+    if (jb.i[7] != ej[0].i[7] || jb.i[3] != ej[0].i[3] || jb.i[4] != ej[0].i[4] || jb.f[0] != ej[0].f[0]) g.uniform = 0;
+    n_lists += jb.i[1];
+    if (jb.i[11] > max_pairs) max_pairs = jb.i[11];
+  }
+  if (!g.uniform) g.smem = 0;
+  if (g.smem > 200 * 1024) { g.uniform = 0; g.smem = 0; }
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+  // parameter-driven column walk: large same-order meshes.  POCKIT_B200_EXPAND=columns forces the
+  // persistent kernel, =params insists on the parameter-driven one.
+  const long long n0 = ej[0].i[3], r0 = ej[0].i[4];
+  const size_t xsm = sizeof(double) * (size_t)(n0 * r0 + (PK_XC_THREADS / n0 + 2) * r0);
+  bool cols = g.uniform && count <= PK_XC_JOBS && n_lists <= PK_XC_LISTS && max_pairs >= 8 * PK_XC_THREADS &&
+              e->dims.batch <= 65535 && xsm <= 200 * 1024;
+  if (const char* env = getenv("POCKIT_B200_EXPAND")) {
+    if (!strcmp(env, "params") && !cols) return fail("POCKIT_B200_EXPAND=params: jobs do not fit the parameter-driven kernel");
+    if (!strcmp(env, "columns")) cols = false;
+  }
+  if (cols) {
+    g.cols = true;
+    g.xc_smem = xsm;
+    PkXcParams& q = g.xc;
+    memset(&q, 0, sizeof(q));
+    q.n = (int)n0; q.rows = (int)r0; q.n_jobs = (int)count; q.unit = ej[0].i[7]; q.sign = ej[0].f[0];
+    int li = 0;
+    for (int j = 0; j < q.n_jobs; ++j) {
+      const pk_job& jb = ej[j];
+      q.job[j].lam0 = jb.i[2]; q.job[j].node0 = jb.i[6]; q.job[j].width = jb.i[8]; q.job[j].Lm = jb.i[10];
+      q.job[j].step = (int)jb.i[5]; q.job[j].pairs = (unsigned)jb.i[11];
+      for (long long l = 0; l < jb.i[1]; ++l, ++li) {
+        const size_t at = (size_t)(jb.i[0] + 2 * l);
+        if (at + 1 >= e->h_ipool.size()) return fail("expand job: list table outside the integer pool");
+        q.list[li].dst = e->h_ipool[at];
+        q.list[li].wbase = e->h_ipool[at + 1];
+        q.list[li].job = j;
+      }
+    }
+    q.n_lists = li;
+    g.xc_gx = (unsigned)((max_pairs + PK_XC_THREADS - 1) / PK_XC_THREADS);
+    auto kern = g.lam ? (const void*)pk_expand_cols<true> : (const void*)pk_expand_cols<false>;
+    if (xsm > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+    return 0;
+  }
+  if (g.smem > 48 * 1024)
+    CK(cudaFuncSetAttribute(pk_expand_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  CK(cudaMalloc((void**)&g.prefix, sizeof(long long) * prefix.size()));
+  CK(cudaMemcpy(g.prefix, prefix.data(), sizeof(long long) * prefix.size(), cudaMemcpyHostToDevice));
+  // one resident wave: SMs x blocks/SM, shared between the instances of a batch
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_expand_blocks, PK_THREADS, g.smem));
+  const long long wave = (long long)(per_sm > 0 ? per_sm : 1) * sms;
+  const long long need = (prefix.back() + PK_THREADS - 1) / PK_THREADS;
+  long long gx = (wave + e->dims.batch - 1) / e->dims.batch;
+  if (gx < 1) gx = 1;
+  g.blocks = need < gx ? need : gx;
+  return 0;
+}
+
 extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d) {
   if (!e || !d) return fail("pk_engine_load_mode: null argument");
   if (mode < 0 || mode >= PK_N_MODES) return fail("pk_engine_load_mode: bad mode");
@@ -291,6 +397,15 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
   }
   ms.n_scalar = d->n_scalar;
   ms.n_out = d->n_out;
+  ms.grad_off = d->grad_offset;
+  ms.grad_cnt = d->grad_count;
+  if (ms.grad_off < 0 || ms.grad_cnt < 0 || ms.grad_off + ms.grad_cnt > d->n_out) return fail("pk_engine_load_mode: gradient range outside the output");
+  for (int k = 0; k < PK_N_CALLBACKS; ++k) {
+    ms.sub_off[k] = d->sub_offset[k];
+    ms.sub_cnt[k] = d->sub_count[k];
+    if (ms.sub_off[k] < 0 || ms.sub_cnt[k] < 0 || ms.sub_off[k] + ms.sub_cnt[k] > d->n_out) return fail("pk_engine_load_mode: callback range outside the output");
+  }
+  for (auto& other : e->mode) other.in_set = false;
   CK(cudaMalloc((void**)&ms.OUT, sizeof(double) * (size_t)e->dims.batch * (size_t)(d->n_out > 0 ? d->n_out : 1)));
   {
     const size_t ns = sizeof(double) * (size_t)e->dims.batch * (size_t)(d->n_scalar > 0 ? d->n_scalar : 1);
@@ -298,9 +413,16 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     CK(cudaMalloc((void**)&ms.S, ns));
     CK(cudaMalloc((void**)&ms.W, nw));
     CK(cudaMemset(ms.S, 0, ns));
-    CK(cudaStreamCreateWithFlags(&ms.stream, cudaStreamNonBlocking));
+    // the latency-bound chains (small callbacks, and the side chain of the large ones) get the higher
+    // priority: their few blocks must not queue behind the thousands of blocks of a block expansion
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const char* pe = getenv("POCKIT_B200_PRIORITY");
+    const bool use_prio = !(pe && pe[0] == '0');
+    const bool big = mode == PK_MODE_JACOBIAN || mode == PK_MODE_HESSIAN || mode == PK_MODE_SET;
+    CK(cudaStreamCreateWithPriority(&ms.stream, cudaStreamNonBlocking, use_prio && !big ? prio_hi : prio_lo));
     CK(cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&ms.side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&ms.side, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaEventCreateWithFlags(&ms.side_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ms.side_join, cudaEventDisableTiming));
   }
@@ -317,33 +439,18 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     }
   }
   if (build_block_map(d->jobs[PK_STAGE_GENERIC], d->n_jobs[PK_STAGE_GENERIC], 1, PK_CHUNK, e->dims.batch, &ms.gen_job, &ms.gen_chunk, &ms.gen_blocks)) return 1;
-  if (d->n_jobs[PK_STAGE_EXPAND] > 0) {
+  // block expansion: consecutive jobs with the same multiplier use form a group (the set pipeline
+  // holds the Jacobian's and the Hessian's jobs), each launched with the best kernel for it
+  {
     const pk_job* ej = d->jobs[PK_STAGE_EXPAND];
-    std::vector<long long> prefix(1, 0);
-    ms.exp_uniform = 1;
-    for (long long j = 0; j < d->n_jobs[PK_STAGE_EXPAND]; ++j) {
-      const pk_job& jb = ej[j];
-      if (jb.i[11] >= (1LL << 31) || jb.i[1] * jb.i[11] >= (1LL << 32)) return fail("expand job too large for 32-bit unit indices");
-      prefix.push_back(prefix.back() + jb.i[1] * jb.i[11]);
-      const size_t sm = sizeof(double) * (size_t)(jb.i[3] * jb.i[4]);
-      if (sm > ms.exp_smem) ms.exp_smem = sm;
-      if (jb.i[7] != ej[0].i[7] || jb.i[3] != ej[0].i[3] || jb.i[4] != ej[0].i[4] || jb.f[0] != ej[0].f[0]) ms.exp_uniform = 0;
+    const long long nj = d->n_jobs[PK_STAGE_EXPAND];
+    for (long long a = 0; a < nj;) {
+      long long b = a + 1;
+      while (b < nj && (ej[b].flags & PK_F_LAM) == (ej[a].flags & PK_F_LAM)) ++b;
+      ms.exp.emplace_back();
+      if (setup_expand_group(e, ej + a, a, b - a, ms.exp.back())) return 1;
+      a = b;
     }
-    if (!ms.exp_uniform) ms.exp_smem = 0;
-    if (ms.exp_smem > 200 * 1024) { ms.exp_uniform = 0; ms.exp_smem = 0; }
-    if (ms.exp_smem > 48 * 1024)
-      CK(cudaFuncSetAttribute(pk_expand_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.exp_smem));
-    CK(cudaMalloc((void**)&ms.exp_prefix, sizeof(long long) * prefix.size()));
-    CK(cudaMemcpy(ms.exp_prefix, prefix.data(), sizeof(long long) * prefix.size(), cudaMemcpyHostToDevice));
-    // one resident wave: SMs x blocks/SM, shared between the instances of a batch
-    int per_sm = 0, sms = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_expand_blocks, PK_THREADS, ms.exp_smem));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-    long long wave = (long long)(per_sm > 0 ? per_sm : 1) * sms;
-    long long need = (prefix.back() + PK_THREADS - 1) / PK_THREADS;
-    long long gx = (wave + e->dims.batch - 1) / e->dims.batch;
-    if (gx < 1) gx = 1;
-    ms.exp_blocks = need < gx ? need : gx;
   }
   for (long long j = 0; j < d->n_jobs[PK_STAGE_DEFECT]; ++j) {
     const pk_job& jb = d->jobs[PK_STAGE_DEFECT][j];
@@ -400,7 +507,24 @@ static PkCtx make_ctx(pk_engine* e, const ModeState& ms) {
   return cx;
 }
 
+static bool use_pipeline(pk_engine* e, const int* modes, int n_modes);
+
 static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+static void launch_expand(const ModeState& ms, const PkCtx& cx, int B, cudaStream_t st) {
+  for (const ExpandGroup& g : ms.exp) {
+    const pk_job* jobs = ms.jobs[PK_STAGE_EXPAND] + g.first;
+    if (g.cols) {
+      const dim3 grid(g.xc_gx, (unsigned)g.xc.n_lists, B);
+      if (g.lam)
+        pk_expand_cols<true><<<grid, PK_XC_THREADS, g.xc_smem, st>>>(cx, g.xc);
+      else
+        pk_expand_cols<false><<<grid, PK_XC_THREADS, g.xc_smem, st>>>(cx, g.xc);
+    } else {
+      pk_expand_blocks<<<dim3((unsigned)g.blocks, B), PK_THREADS, g.smem, st>>>(cx, jobs, (int)g.count, g.prefix, g.uniform);
+    }
+  }
+}
 
 // stage_mask selects which parts run (bit s = job stage s, bit PK_N_STAGES = node programs,
 // bit PK_N_STAGES + 1 = system program); used by pk_time to attribute time.
@@ -408,8 +532,14 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
   ModeState& ms = e->mode[mode];
   if (!ms.loaded) return fail("mode not loaded");
   const int B = e->dims.batch;
+  if (mode == PK_MODE_SET)
+    for (int k = 0; k < PK_N_CALLBACKS; ++k) e->mode[k].in_set = true;
+  else
+    ms.in_set = false;
   PkCtx cx = make_ctx(e, ms);
-  if (stage_mask & (1u << PK_N_STAGES)) {
+  auto on = [&](int stage) { return (stage_mask & (1u << stage)) != 0; };
+  if (on(PK_N_STAGES)) {
+    tr(e, mode, 6, 0, st);
     for (size_t p = 0; p < ms.node_kernels.size(); ++p) {
       const pk_node_program& np_ = ms.node_programs[p];
       const double* tm = e->dpool + np_.tm_offset;
@@ -420,81 +550,95 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
       CK(cudaLaunchKernel((void*)ms.node_kernels[p], dim3(blocks_for(threads, 128)), dim3(128), args, 0, st));
       ++e->launches;
     }
+    tr(e, mode, 6, 1, st);
   }
-  if ((stage_mask & (1u << PK_STAGE_REDUCE)) && ms.n_jobs[PK_STAGE_REDUCE]) {
+  // The block expansion only reads the node table, so it starts right behind the per-node programs
+  // on `st`; everything latency-bound -- reductions, system program, defects, the small slot runs,
+  // the gradient gather -- runs as one chain on the side stream and hides behind it.
+  const bool run_exp = on(PK_STAGE_EXPAND) && !ms.exp.empty();
+  const bool small = (on(PK_STAGE_REDUCE) && ms.n_jobs[PK_STAGE_REDUCE]) || (on(PK_N_STAGES + 1) && ms.sys_kernel) ||
+                     (on(PK_STAGE_DEFECT) && ms.n_jobs[PK_STAGE_DEFECT]) || (on(PK_STAGE_GENERIC) && ms.gen_blocks) ||
+                     (ms.grad_cnt && (on(PK_STAGE_GRAD_RANGE) || on(PK_STAGE_GRAD_SCALAR)));
+  const bool fork = run_exp && small;
+  cudaStream_t ss = fork ? ms.side : st;  // stream of the small chain
+  if (fork) {
+    CK(cudaEventRecord(ms.side_fork, st));
+    CK(cudaStreamWaitEvent(ms.side, ms.side_fork, 0));
+  }
+  if (run_exp) {
+    tr(e, mode, PK_STAGE_EXPAND, 0, st);
+    if (e->chain && e->chain_last >= 0) CK(cudaStreamWaitEvent(st, e->chain_ev[e->chain_last], 0));
+    launch_expand(ms, cx, B, st);
+    if (e->chain) { CK(cudaEventRecord(e->chain_ev[mode], st)); e->chain_last = mode; }
+    e->launches += (long long)ms.exp.size();
+    tr(e, mode, PK_STAGE_EXPAND, 1, st);
+  }
+  if (on(PK_STAGE_REDUCE) && ms.n_jobs[PK_STAGE_REDUCE]) {
     const long long warps = ms.n_jobs[PK_STAGE_REDUCE] * (long long)B;
     if (ms.red_parts)
-      pk_reduce_rows_block<<<(unsigned)(warps * ms.red_parts), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B,
+      pk_reduce_rows_block<<<(unsigned)(warps * ms.red_parts), PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B,
                                                                                    ms.red_parts, ms.red_partial, ms.red_ticket);
     else
-      pk_reduce_rows<<<blocks_for(warps * 32, PK_THREADS), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B);
+      pk_reduce_rows<<<blocks_for(warps * 32, PK_THREADS), PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B);
     ++e->launches;
+    tr(e, mode, PK_STAGE_REDUCE, 1, ss);
   }
-  if ((stage_mask & (1u << (PK_N_STAGES + 1))) && ms.sys_kernel) {
+  if (on(PK_N_STAGES + 1) && ms.sys_kernel) {
     int Bi = B;
     void* args[] = {&e->X, &ms.S, &ms.OUT, &Bi};
-    CK(cudaLaunchKernel((void*)ms.sys_kernel, dim3(blocks_for(B, 64)), dim3(64), args, 0, st));
+    CK(cudaLaunchKernel((void*)ms.sys_kernel, dim3(blocks_for(B, 64)), dim3(64), args, 0, ss));
     ++e->launches;
+    tr(e, mode, 7, 1, ss);
   }
-  if ((stage_mask & (1u << PK_STAGE_DEFECT)) && ms.n_jobs[PK_STAGE_DEFECT]) {
+  if (on(PK_STAGE_DEFECT) && ms.n_jobs[PK_STAGE_DEFECT]) {
     dim3 grid(blocks_for(ms.max_defect_rows * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_DEFECT]);
     if (ms.def_table) {
-      pk_defects<<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+      pk_defects<<<grid, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
       ++e->launches;
     }
     if (ms.def_fast) {
       if (ms.idx32)
-        pk_defects_blocks<unsigned><<<grid, PK_THREADS, ms.def_smem, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+        pk_defects_blocks<unsigned><<<grid, PK_THREADS, ms.def_smem, ss>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
       else
-        pk_defects_blocks<unsigned long long><<<grid, PK_THREADS, ms.def_smem, st>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+        pk_defects_blocks<unsigned long long><<<grid, PK_THREADS, ms.def_smem, ss>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
       ++e->launches;
     }
+    tr(e, mode, PK_STAGE_DEFECT, 1, ss);
   }
-  const bool run_gen = (stage_mask & (1u << PK_STAGE_GENERIC)) && ms.gen_blocks;
-  const bool run_exp = (stage_mask & (1u << PK_STAGE_EXPAND)) && ms.exp_blocks;
-  if (run_gen && run_exp) {
-    // independent of each other (both only read the tables): the latency-bound small runs go to a
-    // side stream and overlap the HBM-bound block expansion
-    CK(cudaEventRecord(ms.side_fork, st));
-    CK(cudaStreamWaitEvent(ms.side, ms.side_fork, 0));
+  if (on(PK_STAGE_GENERIC) && ms.gen_blocks) {
     if (ms.idx32)
-      pk_generic_jobs<unsigned><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ms.side>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
+      pk_generic_jobs<unsigned><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
     else
-      pk_generic_jobs<unsigned long long><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ms.side>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
-    CK(cudaEventRecord(ms.side_join, ms.side));
-    pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], (int)ms.n_jobs[PK_STAGE_EXPAND], ms.exp_prefix, ms.exp_uniform);
-    CK(cudaStreamWaitEvent(st, ms.side_join, 0));
-    e->launches += 2;
-  } else if (run_gen) {
-    if (ms.idx32)
-      pk_generic_jobs<unsigned><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
-    else
-      pk_generic_jobs<unsigned long long><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
+      pk_generic_jobs<unsigned long long><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
     ++e->launches;
-  } else if (run_exp) {
-    pk_expand_blocks<<<dim3((unsigned)ms.exp_blocks, B), PK_THREADS, ms.exp_smem, st>>>(cx, ms.jobs[PK_STAGE_EXPAND], (int)ms.n_jobs[PK_STAGE_EXPAND], ms.exp_prefix, ms.exp_uniform);
-    ++e->launches;
+    tr(e, mode, PK_STAGE_GENERIC, 1, ss);
   }
-  if (mode == PK_MODE_GRADIENT && (stage_mask & ((1u << PK_STAGE_GRAD_RANGE) | (1u << PK_STAGE_GRAD_SCALAR)))) {
-    CK(cudaMemsetAsync(ms.OUT, 0, sizeof(double) * (size_t)B * (size_t)ms.n_out, st));
+  if (ms.grad_cnt && (on(PK_STAGE_GRAD_RANGE) || on(PK_STAGE_GRAD_SCALAR))) {
+    CK(cudaMemset2DAsync(ms.OUT + ms.grad_off, sizeof(double) * (size_t)ms.n_out, 0, sizeof(double) * (size_t)ms.grad_cnt, (size_t)B, ss));
     if (ms.n_jobs[PK_STAGE_GRAD_RANGE]) {
       dim3 grid(blocks_for(ms.max_grad_count * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_GRAD_RANGE]);
       if (ms.idx32)
-        pk_grad_range<unsigned><<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
+        pk_grad_range<unsigned><<<grid, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
       else
-        pk_grad_range<unsigned long long><<<grid, PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
+        pk_grad_range<unsigned long long><<<grid, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
       ++e->launches;
     }
     if (ms.n_jobs[PK_STAGE_GRAD_SCALAR]) {
       const long long n = ms.n_jobs[PK_STAGE_GRAD_SCALAR] * (long long)B;
-      pk_grad_scalar<<<blocks_for(n, PK_THREADS), PK_THREADS, 0, st>>>(cx, ms.jobs[PK_STAGE_GRAD_SCALAR], (int)ms.n_jobs[PK_STAGE_GRAD_SCALAR], B);
+      pk_grad_scalar<<<blocks_for(n, PK_THREADS), PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GRAD_SCALAR], (int)ms.n_jobs[PK_STAGE_GRAD_SCALAR], B);
       ++e->launches;
     }
+    tr(e, mode, PK_STAGE_GRAD_RANGE, 1, ss);
+  }
+  if (fork) {
+    CK(cudaEventRecord(ms.side_join, ms.side));
+    CK(cudaStreamWaitEvent(st, ms.side_join, 0));
   }
   if (ms.n_compact && stage_mask == ~0u) {
     pk_compact<<<blocks_for(ms.n_compact * B, PK_THREADS), PK_THREADS, 0, st>>>(ms.OUT, ms.OUTC, ms.cp_ptr, ms.cp_perm, ms.n_out,
                                                                                ms.n_compact, B);
     ++e->launches;
+    tr(e, mode, 8, 1, st);
   }
   CK(cudaGetLastError());
   return 0;
@@ -547,6 +691,12 @@ extern "C" int pk_sync(pk_engine* e) {
 static int download_async(pk_engine* e, int mode, double* out, cudaStream_t st) {
   ModeState& ms = e->mode[mode];
   const size_t B = (size_t)e->dims.batch;
+  if (mode < PK_N_CALLBACKS && ms.in_set) {  // the set pipeline produced it: a slice of the combined output
+    const ModeState& set = e->mode[PK_MODE_SET];
+    CK(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)set.sub_cnt[mode], set.OUT + set.sub_off[mode], sizeof(double) * (size_t)set.n_out,
+                         sizeof(double) * (size_t)set.sub_cnt[mode], B, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
   if (ms.n_compact) {
     CK(cudaMemcpyAsync(out, ms.OUTC, sizeof(double) * B * (size_t)ms.n_compact, cudaMemcpyDeviceToHost, st));
   } else if (!ms.dl_runs.empty()) {
@@ -578,6 +728,7 @@ extern "C" int pk_engine_set_output_runs(pk_engine* e, int mode, const int64_t* 
     if (runs[2 * r] < 0 || runs[2 * r + 1] < 0 || runs[2 * r] + runs[2 * r + 1] > ms.n_out)
       return fail("pk_engine_set_output_runs: run outside the output");
   ms.dl_runs.assign(runs, runs + 2 * n_runs);
+  ms.in_set = false;
   return 0;
 }
 
@@ -593,6 +744,7 @@ extern "C" int pk_engine_set_compaction(pk_engine* e, int mode, int64_t n_unique
   ms.cp_ptr = ms.cp_perm = nullptr;
   ms.OUTC = nullptr;
   ms.n_compact = 0;
+  ms.in_set = false;
   if (e->set_graph) {  // the captured set no longer matches
     cudaGraphExecDestroy(e->set_graph);
     e->set_graph = nullptr;
@@ -663,6 +815,23 @@ extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, con
   if (hess && (!lam || !sig)) return fail("pk_eval_set: multipliers required for the Hessian");
   if (pk_upload_x(e, x)) return 1;
   if (hess && pk_upload_multipliers(e, lam, sig)) return 1;
+  if (use_pipeline(e, modes, n_modes)) {
+    // one pipeline for all five; the copies of its slices follow on the same stream, largest first
+    CK(cudaEventRecord(e->fork, e->stream));
+    ModeState& ps = e->mode[PK_MODE_SET];
+    CK(cudaStreamWaitEvent(ps.stream, e->fork, 0));
+    if (launch_mode(e, PK_MODE_SET, ~0u, ps.stream)) return 1;
+    std::vector<int> ord(n_modes);
+    for (int k = 0; k < n_modes; ++k) ord[k] = k;
+    for (int a = 1; a < n_modes; ++a)
+      for (int b = a; b > 0 && ps.sub_cnt[modes[ord[b]]] > ps.sub_cnt[modes[ord[b - 1]]]; --b) std::swap(ord[b], ord[b - 1]);
+    for (int q = 0; q < n_modes; ++q)
+      if (download_async(e, modes[ord[q]], outs[ord[q]], ps.stream)) return 1;
+    CK(cudaEventRecord(ps.done, ps.stream));
+    CK(cudaStreamWaitEvent(e->stream, ps.done, 0));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+  }
   CK(cudaEventRecord(e->fork, e->stream));
   // largest outputs first: their copies keep the copy engine busy while the small modes compute
   std::vector<int> order(n_modes);
@@ -716,8 +885,28 @@ extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float
 // Launch several callbacks at the same x as ONE graph: every mode runs on its own stream (its
 // tables and output buffer are private), forked from and joined to the engine stream, so the
 // latency-bound small callbacks overlap the HBM-bound expansions and the host pays one launch.
+// All five callbacks requested, the set pipeline loaded, and no per-callback output shaping
+// (de-duplicated pattern / mesh shard) in the way: evaluate them as PK_MODE_SET.
+static bool use_pipeline(pk_engine* e, const int* modes, int n_modes) {
+  if (n_modes != PK_N_CALLBACKS || !e->mode[PK_MODE_SET].loaded) return false;
+  const char* env = getenv("POCKIT_B200_SET");
+  if (env && env[0] == '0') return false;  // (the Python layer only loads the pipeline when asked to)
+  unsigned seen = 0;
+  for (int k = 0; k < n_modes; ++k) {
+    if (modes[k] < 0 || modes[k] >= PK_N_CALLBACKS) return false;
+    const ModeState& ms = e->mode[modes[k]];
+    if (ms.n_compact || !ms.dl_runs.empty()) return false;
+    seen |= 1u << modes[k];
+  }
+  return seen == (1u << PK_N_CALLBACKS) - 1;
+}
+
 static int run_set(pk_engine* e, const int* modes, int n_modes) {
   std::vector<int> want(modes, modes + n_modes);
+  const bool pipeline = use_pipeline(e, modes, n_modes);
+  if (pipeline) want.assign(1, PK_MODE_SET);
+  n_modes = (int)want.size();
+  modes = want.data();
   if (!e->set_graph || want != e->set_modes) {
     for (int k = 0; k < n_modes; ++k)
       if (modes[k] < 0 || modes[k] >= PK_N_MODES || !e->mode[modes[k]].loaded) return fail("pk_run_set: mode not loaded");
@@ -728,13 +917,20 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     CK(cudaEventRecord(e->fork, e->stream));
     int rc = 0;
+    std::vector<int> order(want);  // largest outputs first: their expansions head the chain
+    for (int a = 1; a < n_modes; ++a)
+      for (int b = a; b > 0 && e->mode[order[b]].n_out > e->mode[order[b - 1]].n_out; --b) std::swap(order[b], order[b - 1]);
+    const char* ch = getenv("POCKIT_B200_CHAIN");
+    e->chain = !(ch && ch[0] == '0');
+    e->chain_last = -1;
     for (int k = 0; k < n_modes && !rc; ++k) {
-      ModeState& ms = e->mode[modes[k]];
+      ModeState& ms = e->mode[order[k]];
       if (cudaStreamWaitEvent(ms.stream, e->fork, 0) != cudaSuccess) rc = 1;
-      if (!rc) rc = launch_mode(e, modes[k], ~0u, ms.stream);
+      if (!rc) rc = launch_mode(e, order[k], ~0u, ms.stream);
       if (!rc && cudaEventRecord(ms.done, ms.stream) != cudaSuccess) rc = 1;
       if (!rc && cudaStreamWaitEvent(e->stream, ms.done, 0) != cudaSuccess) rc = 1;
     }
+    e->chain = false;
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     if (rc || ce != cudaSuccess || !graph) {
       if (graph) cudaGraphDestroy(graph);
@@ -748,6 +944,11 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
   }
   CK(cudaGraphLaunch(e->set_graph, e->stream));
   e->launches += e->set_launches;
+  // replays do not pass through launch_mode: keep track of where the latest values live
+  if (pipeline)
+    for (int k = 0; k < PK_N_CALLBACKS; ++k) e->mode[k].in_set = true;
+  else
+    for (int k = 0; k < n_modes; ++k) e->mode[want[k]].in_set = false;
   return 0;
 }
 
@@ -773,6 +974,59 @@ extern "C" int pk_time_steps(pk_engine* e, const int* modes, int n_modes, int st
   }
   cudaEventDestroy(a);
   cudaEventDestroy(b);
+  return 0;
+}
+
+// Device-side timeline of one evaluation set launched on the per-mode streams (no graph): the
+// engine stream is first kept busy with a few L2-flush fills so that the host gets ahead and the
+// marks show dependency resolution on the device, not host launch latency.  rows = (mode, tag,
+// edge, microseconds since the set was released); tags as in tr().
+extern "C" int pk_timeline(pk_engine* e, const int* modes, int n_modes, double* rows, int max_rows, int* n_rows) {
+  if (!e || !modes || n_modes < 1 || !rows || !n_rows) return fail("pk_timeline: bad argument");
+  CK(cudaSetDevice(e->device));
+  for (int k = 0; k < n_modes; ++k)
+    if (modes[k] < 0 || modes[k] >= PK_N_MODES || !e->mode[modes[k]].loaded) return fail("pk_timeline: mode not loaded");
+  std::vector<pk_engine::Mark> marks;
+  cudaEvent_t base, end;
+  CK(cudaEventCreate(&base));
+  CK(cudaEventCreate(&end));
+  CK(cudaStreamSynchronize(e->stream));
+  for (int k = 0; k < 4; ++k)
+    if (pk_flush_l2(e)) return 1;
+  CK(cudaEventRecord(base, e->stream));
+  CK(cudaEventRecord(e->fork, e->stream));
+  e->trace = &marks;
+  int rc = 0;
+  for (int k = 0; k < n_modes && !rc; ++k) {
+    ModeState& ms = e->mode[modes[k]];
+    if (cudaStreamWaitEvent(ms.stream, e->fork, 0) != cudaSuccess) rc = 1;
+    if (!rc) rc = launch_mode(e, modes[k], ~0u, ms.stream);
+    if (!rc && cudaEventRecord(ms.done, ms.stream) != cudaSuccess) rc = 1;
+    if (!rc && cudaStreamWaitEvent(e->stream, ms.done, 0) != cudaSuccess) rc = 1;
+  }
+  e->trace = nullptr;
+  if (rc) return rc;
+  CK(cudaEventRecord(end, e->stream));
+  CK(cudaEventSynchronize(end));
+  int n = 0;
+  for (auto& mk : marks) {
+    float ms_ = 0.f;
+    cudaEventElapsedTime(&ms_, base, mk.ev);
+    if (n < max_rows) {
+      rows[4 * n] = mk.mode; rows[4 * n + 1] = mk.tag; rows[4 * n + 2] = mk.edge; rows[4 * n + 3] = 1000.0 * ms_;
+      ++n;
+    }
+    cudaEventDestroy(mk.ev);
+  }
+  float tot = 0.f;
+  cudaEventElapsedTime(&tot, base, end);
+  if (n < max_rows) {
+    rows[4 * n] = -1; rows[4 * n + 1] = -1; rows[4 * n + 2] = 1; rows[4 * n + 3] = 1000.0 * tot;
+    ++n;
+  }
+  *n_rows = n;
+  cudaEventDestroy(base);
+  cudaEventDestroy(end);
   return 0;
 }
 

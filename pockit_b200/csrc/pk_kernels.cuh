@@ -267,6 +267,84 @@ __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const p
 }
 
 // ---------------------------------------------------------------------------------------------
+// Column walk with everything a thread needs before its first store in the kernel PARAMETERS
+// (constant bank): job geometry and the (dst, W row) of every list.  The persistent kernel above
+// spends its first microseconds on a chain of dependent L2 round trips (job record -> list table
+// -> list value); here the only global loads ahead of the stores are the list value and the
+// interval width, issued before the unit block is staged.  Non-persistent: grid = (chunks of
+// PK_XC_THREADS (interval, column) pairs, lists, instances) -- measured on B200, a write stream
+// of this shape (tools/microbench_write2.cu, "cols 1 unit/thread") is what gets closest to the
+// plain-fill ceiling at ~100 MB.  Multipliers of the block's intervals are staged in shared memory.
+// Same-order meshes only (all jobs share unit block, shape and sign), <= PK_XC_JOBS jobs,
+// <= PK_XC_LISTS lists; everything else takes pk_expand_blocks.
+#define PK_XC_THREADS 128
+#define PK_XC_JOBS 8
+#define PK_XC_LISTS 96
+struct PkXcJob {
+  long long lam0;    // multiplier row of the first block row (LAM only)
+  long long node0;   // first node of the first interval
+  long long width;   // dpool offset of the interval widths
+  long long Lm;      // nodes per W row
+  int step;          // nodes per interval step
+  unsigned pairs;    // intervals * n
+};
+struct PkXcList {
+  long long dst, wbase;
+  int job, pad;
+};
+struct PkXcParams {
+  int n, rows, n_lists, n_jobs;
+  long long unit;  // dpool offset of the unit block
+  double sign;
+  PkXcJob job[PK_XC_JOBS];
+  PkXcList list[PK_XC_LISTS];
+};
+
+template <bool LAM>
+__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const __grid_constant__ PkXcParams prm) {
+  extern __shared__ double smem_d[];
+  const int n = prm.n, rows = prm.rows;
+  const int bn = n * rows;
+  double* u_s = smem_d;        // [bn] sign-folded unit block
+  double* lam_s = smem_d + bn; // multipliers of the intervals this block touches
+  const PkXcList& L = prm.list[blockIdx.y];
+  const PkXcJob& J = prm.job[L.job];
+  const int b = blockIdx.z;
+  const unsigned t0 = blockIdx.x * PK_XC_THREADS;
+  if (t0 >= J.pairs) return;  // lists of a shorter job
+  const unsigned t = t0 + threadIdx.x;
+  const bool live = t < J.pairs;
+  const unsigned K = (live ? t : J.pairs - 1) / (unsigned)n;
+  const unsigned cc = (live ? t : J.pairs - 1) - K * (unsigned)n;
+  const unsigned K0 = t0 / (unsigned)n;
+  // the two loads the stores depend on go out first
+  const double sv = cx.W[L.wbase + (long long)b * J.Lm + J.node0 + (long long)K * J.step + cc];
+  const double w = cx.dpool[J.width + K];
+  {
+    const double* unit = cx.dpool + prm.unit;
+    for (int q = threadIdx.x; q < bn; q += PK_XC_THREADS) u_s[q] = prm.sign * unit[q];
+    if (LAM) {
+      unsigned tl = t0 + PK_XC_THREADS - 1;
+      if (tl >= J.pairs) tl = J.pairs - 1;
+      const int n_lam = (int)(tl / (unsigned)n - K0 + 1) * rows;
+      const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K0 * rows;
+      for (int q = threadIdx.x; q < n_lam; q += PK_XC_THREADS) lam_s[q] = lam[q];
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + L.dst + (long long)K * bn + cc;
+  const double* u = u_s + cc;
+  const double* lm = lam_s + (K - K0) * rows;
+#pragma unroll 4
+  for (int r = 0; r < rows; ++r) {
+    double v = (u[r * n] * w) / 2.0;
+    if (LAM) v = v * lm[r];
+    out[r * n] = v * sv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double pk_list_at(const PkCtx& cx, const double* Sb, int b, int scalar, int unit,
                                              long long src, long long lm, long long c_lo, long long k) {
   if (unit) return 1.0;

@@ -18,7 +18,8 @@ from . import plan as P
 __all__ = ["Engine", "load_library", "library_path", "PinnedArray"]
 
 N_STAGES = 6
-N_MODES = 5
+N_MODES = 6  # five callbacks + the fused set pipeline (plan.SET)
+N_CALLBACKS = 5
 
 
 class _Job(C.Structure):
@@ -43,6 +44,8 @@ class _ModeDesc(C.Structure):
         ("n_node_programs", C.c_int32), ("node_programs", C.POINTER(_NodeProgram)), ("system_kernel", C.c_char_p),
         ("table_symbol", C.c_char_p), ("table", C.POINTER(C.c_int64)), ("n_table_entries", C.c_int64),
         ("n_scalar", C.c_int64), ("n_out", C.c_int64), ("jobs", C.c_void_p * N_STAGES), ("n_jobs", C.c_int64 * N_STAGES),
+        ("grad_offset", C.c_int64), ("grad_count", C.c_int64),
+        ("sub_offset", C.c_int64 * N_CALLBACKS), ("sub_count", C.c_int64 * N_CALLBACKS),
     ]
 
 
@@ -93,6 +96,7 @@ def load_library():
         "pk_time": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
         "pk_time_steps": ([vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "pk_kernel_launches": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "pk_timeline": ([vp, C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.POINTER(C.c_int)], C.c_int),
         "pk_flush_l2": ([vp], C.c_int),
         "pk_alloc_host": ([C.c_size_t], vp),
         "pk_free_host": ([vp], None),
@@ -102,7 +106,7 @@ def load_library():
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = args, res
-    if lib.pk_abi_version() != 1:
+    if lib.pk_abi_version() != 2:
         raise RuntimeError("libpockit_b200.so: ABI version mismatch")
     _LIB = lib
     return lib
@@ -140,16 +144,23 @@ class Engine:
         self.plan = P.DevicePlan(lowering, self.B, fastmath, shard=shard,
                                  fused=shard is None and os.environ.get("POCKIT_B200_FUSED", "0") == "1")
         self.fin = {}
-        for m in range(N_MODES):
+        # The fused set pipeline (plan.SET: one per-node program, one reduction, one system program for
+        # all five callbacks) is opt-in, POCKIT_B200_SET=1: measured on B200 (round 1, tools/probe3.py) it
+        # is SLOWER than five concurrent per-callback pipelines -- robot_arm LGR 2000x20 76 vs 67 us per set,
+        # humanoid 100 k nodes 154 vs 145 us -- because its single chain of small kernels queues behind the
+        # block expansions instead of overlapping them.  Needs a whole plan (no mesh shard / fused walk).
+        self.has_set = shard is None and not self.plan.fused and os.environ.get("POCKIT_B200_SET", "0") == "1"
+        self._mode_ids = list(range(N_CALLBACKS)) + ([P.SET] if self.has_set else [])
+        for m in self._mode_ids:
             self.plan.mode(m)
-        for m in range(N_MODES):
+        for m in self._mode_ids:
             self.fin[m] = self.plan.finalize(m)
         lo = lowering
-        self.n_out = {m: self.fin[m]["n_out"] for m in range(N_MODES)}  # slots on the device
+        self.n_out = {m: self.fin[m]["n_out"] for m in self._mode_ids}  # slots on the device
         self.n_host = dict(self.n_out)  # values the host receives (smaller with a de-duplicated pattern)
         self.compacted = set()  # modes whose duplicates are summed on the device
         dims = _Dims(
-            1, self.B, lo.r_s, lo.m, lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c,
+            2, self.B, lo.r_s, lo.m, lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c,
             max(1, max(f["n_scalar"] for f in self.fin.values())),
             max(1, max(f["n_table"] for f in self.fin.values())), self.plan.n_fixed,
         )
@@ -218,6 +229,10 @@ class Engine:
         d.n_table_entries = len(table)
         d.n_scalar = f["n_scalar"]
         d.n_out = f["n_out"]
+        d.grad_offset, d.grad_count = (int(v) for v in f["grad_range"])
+        if mode == P.SET:
+            for k in range(N_CALLBACKS):
+                d.sub_offset[k], d.sub_count[k] = (int(v) for v in f["sub_range"][k])
         keep = []
         for s in range(N_STAGES):
             arr = np.ascontiguousarray(f["jobs"][s])
@@ -232,6 +247,15 @@ class Engine:
                 raise RuntimeError(f"mode {P.MODES[mode]} is evaluated by rank 0 of the sharded mesh, not by rank {self.shard[0]}")
             if not (len(runs) == 1 and runs[0][0] == 0 and runs[0][1] == f["n_out"]):
                 self._check(self.lib.pk_engine_set_output_runs(self._h, mode, _ptr(np.ascontiguousarray(runs)), len(runs)))
+
+    def _load_for_set(self, modes):
+        """Load what a set evaluation of ``modes`` needs: the modes themselves and, when all five
+        callbacks are asked for on a whole (unsharded, uncompacted) plan, the fused set pipeline,
+        which the engine then runs instead of five separate pipelines."""
+        for m in modes:
+            self.load(m)
+        if self.has_set and sorted(modes) == list(range(N_CALLBACKS)) and not self.compacted:
+            self.load(P.SET)
 
     # ------------------------------------------------------------------ host-to-host callbacks
     def _x(self, x) -> np.ndarray:
@@ -293,8 +317,7 @@ class Engine:
         if modes is None:
             modes = [P.OBJ, P.GRAD, P.CONS, P.JAC] + ([P.HESS] if fct_c is not None else [])
         modes = list(modes)
-        for m in modes:
-            self.load(m)
+        self._load_for_set(modes)
         x = self._x(x)
         lam = sig = None
         if P.HESS in modes:
@@ -376,8 +399,7 @@ class Engine:
 
     def run_set(self, modes):
         """Enqueue several callbacks at the uploaded x as one graph (modes overlap)."""
-        for m in modes:
-            self.load(m)
+        self._load_for_set(modes)
         arr = (C.c_int * len(modes))(*modes)
         self._check(self.lib.pk_run_set(self._h, arr, len(modes)))
 
@@ -399,12 +421,21 @@ class Engine:
 
     def time_steps(self, modes, steps: int, flush_l2: bool = True):
         """Per-step CUDA-event times (ms) of running ``modes`` back to back, inputs resident in HBM."""
-        for m in modes:
-            self.load(m)
+        self._load_for_set(modes)
         arr = (C.c_int * len(modes))(*modes)
         out = (C.c_float * steps)()
         self._check(self.lib.pk_time_steps(self._h, arr, len(modes), steps, int(flush_l2), out))
         return list(out)
+
+    def timeline(self, modes):
+        """Device-side timeline of one evaluation set: list of (mode, tag, edge, microseconds)."""
+        for m in modes:
+            self.load(m)
+        arr = (C.c_int * len(modes))(*modes)
+        rows = np.zeros((256, 4))
+        n = C.c_int()
+        self._check(self.lib.pk_timeline(self._h, arr, len(modes), _ptr(rows), 256, C.byref(n)))
+        return [(int(r[0]), int(r[1]), int(r[2]), float(r[3])) for r in rows[: n.value]]
 
     def flush_l2(self):
         self._check(self.lib.pk_flush_l2(self._h))

@@ -31,8 +31,13 @@ from .emit import PRELUDE, CExpr, emit_block
 from .phase import BcType, Segment
 from .system import SysList, SysSegment, SystemLowering
 
-MODES = ("objective", "constraints", "gradient", "jacobian", "hessian")
-OBJ, CONS, GRAD, JAC, HESS = range(5)
+MODES = ("objective", "constraints", "gradient", "jacobian", "hessian", "set")
+OBJ, CONS, GRAD, JAC, HESS, SET = range(6)
+# SET = all five callbacks at one (x, lambda, sigma) as ONE pipeline: a single per-node program
+# evaluates every leaf once (the Hessian's leaves are a superset of the others'), one reduction and
+# one system program feed all consumers, and the outputs land in one buffer laid out
+# [objective | gradient | constraints | Jacobian values | Hessian values] (SET_ORDER).
+SET_ORDER = (OBJ, GRAD, CONS, JAC, HESS)
 ST_REDUCE, ST_DEFECT, ST_GENERIC, ST_EXPAND, ST_GRAD_RANGE, ST_GRAD_SCALAR = range(6)
 J_CONST, J_KRON, J_EXPAND_TABLE, J_SCALED, J_SYS, J_OUTER, J_TRIL = range(7)
 F_A_SCALAR, F_B_SCALAR, F_A_UNIT, F_B_UNIT, F_LAM = 1, 2, 4, 8, 16
@@ -129,6 +134,10 @@ class ModePlan:
         self.src = None
         self.expand_groups: dict = {}
         self.owned_runs: Optional[list] = None  # mesh shard: (offset, count) runs of the output computed here
+        self.sub = mode   # callback currently being planned (differs from `mode` only inside SET)
+        self.base = 0     # first output slot of that callback
+        self.sub_range: dict = {}  # SET: callback -> (offset, count) inside the combined output
+        self.grad_range = (0, 0)   # output slots the gradient gather-sums into (zeroed first)
         self._build()
         if owner.shard is not None:
             self._shard(*owner.shard)
@@ -296,33 +305,48 @@ class ModePlan:
 
     # ---------------------------------------------------------------- build per mode
     def _build(self):
-        lo = self.owner.lo
-        mode = self.mode
-        if mode == OBJ:
-            self.n_out = 1
-            self._need_system_value(lo.F_o, "o", lo.which_o)
-        elif mode == CONS:
-            self.n_out = lo.m
-            for i, fn in enumerate(lo.F_c):
-                self.sys_need[Leaf("sF", ("c", i))] = -1 - i  # written straight to the output
-            self._need_integrals(lo.which_c)
-            self._constraints()
-        elif mode == GRAD:
-            self.n_out = lo.r_s
-            self._need_integrals(lo.which_o)
-            self._gradient()
-        elif mode == JAC:
-            self.n_out = lo.nnz_jac
-            self._need_integrals(lo.which_c)
-            self._slots(lo.jac_segments)
+        if self.mode == SET:
+            if self.owner.shard is not None or self.owner.fused:
+                raise ValueError("the set pipeline is not planned for mesh shards / the fused variant")
+            off = 0
+            for sub in SET_ORDER:
+                self.sub, self.base = sub, off
+                count = self._build_one(sub)
+                self.sub_range[sub] = (off, count)
+                off += count
+            self.n_out = off
         else:
-            self.n_out = lo.nnz_hess_o + lo.nnz_hess_c
-            self._need_integrals([a | b for a, b in zip(lo.which_o, lo.which_c)])
-            self._slots(lo.hess_o_segments + lo.hess_c_segments)
+            self.n_out = self._build_one(self.mode)
+            self.sub_range[self.mode] = (0, self.n_out)
         self._integral_rows()
 
+    def _build_one(self, mode: int) -> int:
+        """Plan callback ``mode`` with its outputs starting at slot ``self.base``; returns their count."""
+        lo = self.owner.lo
+        if mode == OBJ:
+            self._need_system_value(lo.F_o, "o", lo.which_o)
+            return 1
+        if mode == CONS:
+            for i, fn in enumerate(lo.F_c):
+                self.sys_need[Leaf("sF", ("c", i))] = -1 - (self.base + i)  # written straight to the output
+            self._need_integrals(lo.which_c)
+            self._constraints()
+            return lo.m
+        if mode == GRAD:
+            self._need_integrals(lo.which_o)
+            self._gradient()
+            self.grad_range = (self.base, lo.r_s)
+            return lo.r_s
+        if mode == JAC:
+            self._need_integrals(lo.which_c)
+            self._slots(lo.jac_segments)
+            return lo.nnz_jac
+        self._need_integrals([a | b for a, b in zip(lo.which_o, lo.which_c)])
+        self._slots(lo.hess_o_segments + lo.hess_c_segments)
+        return lo.nnz_hess_o + lo.nnz_hess_c
+
     def _need_system_value(self, fn, tag, which):
-        self.sys_need[Leaf("sF", (tag,))] = -1
+        self.sys_need[Leaf("sF", (tag,))] = -1 - self.base
         self._need_integrals(which)
 
     def _need_integrals(self, which):
@@ -358,7 +382,7 @@ class ModePlan:
         lo, own = self.owner.lo, self.owner
         for pi, p in enumerate(lo.phases):
             col = p.col
-            base = lo.con_base[pi]
+            base = self.base + lo.con_base[pi]
             fd_rows = []
             for i in range(p.n_x):
                 t = Term(Leaf("F", ("d", i)))
@@ -411,11 +435,11 @@ class ModePlan:
             for n, (row, lm, c_lo, g) in enumerate(contrib):
                 rec_rows[n] = row[1]
                 flat += [0, lm, c_lo, g]
-            rec = self.job(ST_GRAD_RANGE, i0=dst, i1=count, i3=len(contrib))
+            rec = self.job(ST_GRAD_RANGE, i0=self.base + dst, i1=count, i3=len(contrib))
             rec["contrib"] = (flat, rec_rows)  # table-row bases are patched in at finalisation
         for dst, contrib in scalars.items():
             flat = [v for pair in contrib for v in pair]
-            self.job(ST_GRAD_SCALAR, i0=dst, i2=pools.int(flat), i3=len(contrib))
+            self.job(ST_GRAD_SCALAR, i0=self.base + dst, i2=pools.int(flat), i3=len(contrib))
 
     # -- Jacobian / Hessian slot runs
     def _post(self, sg: SysSegment):
@@ -427,7 +451,7 @@ class ModePlan:
 
     def _slots(self, segs: list[SysSegment]):
         lo, own = self.owner.lo, self.owner
-        dst = 0
+        dst = self.base
         for sg in segs:
             if sg.count == 0:
                 continue
@@ -489,7 +513,7 @@ class ModePlan:
         pi, p = sg.phase, lo.phases[sg.phase]
         col = p.col
         pools = own.pools
-        has_lam = self.mode == HESS
+        has_lam = self.sub == HESS
         if seg.kind == "const":
             self.job(ST_GENERIC, J_CONST, i0=dst, i1=seg.count, i2=-1, i3=-1, i6=pools.dbl(seg.data))
         elif seg.kind == "kron":
@@ -761,6 +785,7 @@ class DevicePlan:
             source=src, kernels=kernels, sys_kernel=sys_name, table=np.array(mp.table, dtype=np.int64),
             table_symbol=f"pk_tab_{MODES[m]}", jobs=jobs, n_scalar=mp.n_scalar, n_out=mp.n_out,
             n_table=mp.n_table, runs=None if mp.owned_runs is None else np.array(mp.owned_runs, dtype=np.int64).reshape(-1, 2),
+            grad_range=mp.grad_range, sub_range=dict(mp.sub_range),
         )
 
     def _node_kernel(self, mp: ModePlan, pi: int, kname: str) -> str:

@@ -71,10 +71,11 @@ class HostEmu:
         self.lo = system.lowering
         self.dp = P.DevicePlan(self.lo, batch, fused=fused, shard=shard)
         self.B = batch
-        for m in range(5):
+        modes = range(6) if shard is None and not fused else range(5)  # + the fused set pipeline
+        for m in modes:
             self.dp.mode(m)
             self.dp.source(m)
-        self.fin = {m: self.dp.finalize(m) for m in range(5)}
+        self.fin = {m: self.dp.finalize(m) for m in modes}
         self.dpool, self.ipool = self.dp.pools.arrays()
         self.fixed = np.tile(self.dp.fixed_default, (batch, 1)) if fixed is None else np.asarray(fixed, float)
         self.libs = {}
@@ -118,8 +119,9 @@ class HostEmu:
             self._generic(jb, S, W, OUT, LAM, SIG)
         for jb in jobs[P.ST_EXPAND]:
             self._expand(jb, W, OUT, LAM)
-        if mode == P.GRAD:
-            OUT[:] = 0.0
+        if f["grad_range"][1]:
+            g0, gn = f["grad_range"]
+            OUT[:, g0 : g0 + gn] = 0.0
             for jb in jobs[P.ST_GRAD_RANGE]:
                 i = jb["i"]
                 q = self.ipool[i[2] : i[2] + 4 * i[3]].reshape(-1, 4)

@@ -18,10 +18,10 @@ def test_generated_cuda_compiles_for_sm100a(case):
 
     S = build(case)
     dp = P.DevicePlan(S.lowering)
-    for m in range(5):
+    for m in range(6):
         dp.mode(m)
     with tempfile.TemporaryDirectory() as tmp:
-        for m in range(5):
+        for m in range(6):
             src = dp.finalize(m)["source"]
             cu = Path(tmp) / f"mode{m}.cu"
             cu.write_text(src)
@@ -46,4 +46,4 @@ def test_library_exports_declared_symbols():
     for n in sorted(names):
         assert hasattr(lib, n), n
     lib.pk_abi_version.restype = ctypes.c_int
-    assert lib.pk_abi_version() == 1
+    assert lib.pk_abi_version() == 2

@@ -18,12 +18,14 @@ def _dense(rows, cols, vals, shape):
 
 
 @pytest.mark.parametrize("pinned", [False, True])
-def test_evaluate_equals_the_five_callbacks(pinned):
+def test_evaluate_equals_the_five_callbacks(pinned, monkeypatch):
     """One engine call for the whole set returns bit for bit what the five reference-style
-    callbacks return one after the other."""
+    callbacks return one after the other (per-callback pipelines, POCKIT_B200_SET=0; the fused
+    set pipeline is compared in test_gpu_parity.py, to the parity tolerance)."""
     import pockit_b200.lobatto as lob
     from pockit_b200 import problems
 
+    monkeypatch.setenv("POCKIT_B200_SET", "0")
     S = problems.rocket(lob, mesh=30, num_point=8)
     x, lam, sigma = problems.evaluation_point(S, seed=11)
     want = dict(objective=S.objective(x), gradient=S.gradient(x), constraints=S.constraints(x),

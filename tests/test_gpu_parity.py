@@ -129,13 +129,17 @@ def test_size_independent_properties_at_full_size():
     np.testing.assert_allclose(g @ d, fdo, rtol=1e-6, atol=1e-8)
 
 
-def test_evaluation_set_graph_matches_single_callbacks():
-    """pk_run_set (all callbacks at one x as one graph, one stream per mode) must give
-    exactly what the five separate host-to-host callbacks give."""
+@pytest.mark.parametrize("pipeline", ["0", "1"])
+def test_evaluation_set_graph_matches_single_callbacks(pipeline, monkeypatch):
+    """pk_run_set (all callbacks at one x as one graph) against the five separate host-to-host
+    callbacks.  Default (POCKIT_B200_SET=0): one stream per callback, the same kernels ->
+    bit-identical.  POCKIT_B200_SET=1: the fused set pipeline (one per-node program for all five; its
+    single CSE may regroup a product) -> within the parity tolerance."""
     import pockit_b200.lobatto as lob
     from pockit_b200 import plan as P
     from pockit_b200 import problems
 
+    monkeypatch.setenv("POCKIT_B200_SET", pipeline)
     S = problems.rocket(lob, mesh=30, num_point=8)
     x, lam, sigma = problems.evaluation_point(S, seed=5)
     single = {
@@ -143,13 +147,34 @@ def test_evaluation_set_graph_matches_single_callbacks():
         P.JAC: S.jacobian(x), P.HESS: S.hessian(x, lam, sigma),
     }
     eng = S.engine
+    assert eng.has_set == (pipeline == "1")
     modes = [P.OBJ, P.GRAD, P.CONS, P.JAC, P.HESS]
     eng.upload(x, lam, sigma)
     for _ in range(3):  # replays of the captured graph
         eng.run_set(modes)
     eng.sync()
     for m in modes:
-        assert np.array_equal(np.atleast_1d(eng.download(m)), single[m]), P.MODES[m]
+        got = np.atleast_1d(eng.download(m))
+        if pipeline == "0":
+            assert np.array_equal(got, single[m]), P.MODES[m]
+        else:
+            assert_close(got, single[m], P.MODES[m])
+    # a single callback afterwards takes over its output again
+    assert np.array_equal(S.jacobian(x + 1e-3), np.atleast_1d(eng.download(P.JAC)))
+
+
+@pytest.mark.parametrize("name", ["general_lgl", "general_lgr", "rocket_lgl_4x5", "robot_arm_lgr_6x20", "quadrotor_lgl_14x6",
+                                  "humanoid_lgl_4x5", "lqr_lgl_10x10", "static_only_lgl", "no_control_lgr_3x3", "tiny_lgl_1x3"])
+def test_set_pipeline_matches_reference_golden(name, monkeypatch):
+    """System.evaluate through the opt-in fused set pipeline (POCKIT_B200_SET=1) against the real
+    reference's values."""
+    monkeypatch.setenv("POCKIT_B200_SET", "1")
+    S, g = build(name), load(name)
+    x, lam, sigma = g["x"], g["lam"], float(g["sigma"])
+    r = S.evaluate(x.copy(), lam, sigma)
+    assert S.engine.has_set
+    for k in ("objective", "gradient", "constraints", "jacobian", "hessian"):
+        assert_close(r[k], g[k], k)
 
 
 def test_fastmath_model_compiles_and_stays_close():
