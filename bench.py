@@ -16,7 +16,7 @@ nnz_J=12 479 754, nnz_H=12 799 740).
   single-call set evaluation (System.evaluate -> pk_eval_set: one upload, copies
   overlapped with compute); ``e2e.five_callbacks`` is the same set through the five
   reference-style callbacks called one after the other (x uploaded five times).
-* ``roofline`` the dominant kernel (pk_expand_blocks of the Hessian) against the
+* ``roofline`` the dominant kernel (the block expansion of the Hessian) against the
   measured HBM copy bandwidth in MEASURED_PEAKS.json.
 * ``cpu_baseline`` / ``--impl reference``: the CPU oracle port (oracle/pockit_oracle.py,
   a restatement of the reference's NumPy algorithm; the reference itself cannot
@@ -314,7 +314,7 @@ def main():
     _, stages = eng.time(P.HESS, iters=iters, stages=True)
     fin = eng.fin[P.HESS]
     if len(fin["jobs"][P.ST_EXPAND]):  # table/W path (irregular blocks): the stand-alone expansion kernel dominates
-        kernel = "pk_expand_blocks (Hessian mode)"
+        kernel = f"{eng.expand_kernel(P.HESS)} (Hessian mode)"
         k_ms = stages[P.ST_EXPAND] / iters
         jobs = fin["jobs"][P.ST_EXPAND]
         slots = int(sum(int(j["i"][1]) * int(j["i"][11]) * int(j["i"][4]) for j in jobs))
@@ -330,7 +330,7 @@ def main():
         alg_bytes = 8 * (slots + lo.r_s + lo.m + rows_written * lo.phases[0].L_m)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
-    tr = ROOT / "profiles" / "r01_expand_traffic.json"
+    tr = ROOT / "profiles" / "r01_expand_traffic_v8.json"
     if tr.exists():  # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture
         recs = [r for r in json.loads(tr.read_text())["launches"] if r["kernel"].split(" ")[0] == kernel.split(" ")[0]]
         if recs:

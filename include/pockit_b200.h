@@ -145,7 +145,9 @@ int pk_eval_hessian(pk_engine *e, const double *x, const double *lambda /* [B][m
  * point of an x-keyed cache in a solver adapter; Ipopt asks for f, grad f, g, J, H at the same x,
  * optimizer/ipopt.py:41-53): x and the multipliers cross PCIe once, the modes run concurrently and
  * every result is copied back as soon as its mode finishes.  outs[k] receives mode modes[k];
- * lambda / sigma are only read when PK_MODE_HESSIAN is among the modes. */
+ * lambda / sigma are only read when PK_MODE_HESSIAN is among the modes.  x = NULL evaluates at the
+ * point already resident on the device (the previous pk_eval_* / pk_upload_x): the cache's "same x,
+ * another callback" case costs no upload. */
 int pk_eval_set(pk_engine *e, const double *x, const double *lambda, const double *sigma, const int *modes,
                 int n_modes, double *const *outs);
 
@@ -183,7 +185,11 @@ int pk_time_steps(pk_engine *e, const int *modes, int n_modes, int steps, int fl
  * rows[4*i..] = (mode, tag, edge, microseconds); tag = job stage 0..5, 6 node programs, 7 system
  * program, 8 compaction; edge 0 = before, 1 = after; the last row (mode -1) is the whole set */
 int pk_timeline(pk_engine *e, const int *modes, int n_modes, double *rows, int max_rows, int *n_rows);
-int pk_kernel_launches(pk_engine *e, int64_t *count); /* kernels launched so far by this engine */
+/* which block-expansion kernel a loaded mode uses: 0 none, 1 pk_expand_blocks (persistent column
+ * walk, any mix of orders), 2 pk_expand_cols (parameter-driven column walk, same-order meshes) */
+int pk_expand_variant(pk_engine *e, int mode, int *variant);
+int pk_kernel_launches(pk_engine *e, int64_t *count);
+int pk_x_uploads(pk_engine *e, int64_t *count);       /* host-to-device copies of x so far */ /* kernels launched so far by this engine */
 int pk_flush_l2(pk_engine *e);                        /* overwrite a buffer larger than L2 */
 
 /* pinned host memory for zero-copy NumPy views */

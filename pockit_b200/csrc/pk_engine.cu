@@ -91,7 +91,8 @@ struct pk_engine {
   double* flush = nullptr; long long n_flush = 0;
   long long n_out_max = 0;
   ModeState mode[PK_N_MODES];
-  long long launches = 0, set_launches = 0;
+  long long launches = 0, set_launches = 0, x_uploads = 0;
+  bool x_resident = false;
   // pk_timeline: timing events around every launch of a set
   struct Mark { cudaEvent_t ev; int mode, tag, edge; };
   std::vector<Mark>* trace = nullptr;
@@ -652,6 +653,8 @@ extern "C" int pk_upload_x(pk_engine* e, const double* x) {
   memcpy(e->hX, x, n);
   CK(cudaMemcpyAsync(e->X, e->hX, n, cudaMemcpyHostToDevice, e->stream));
   CK(cudaEventRecord(e->x_done, e->stream));
+  e->x_resident = true;
+  ++e->x_uploads;
   return 0;
 }
 
@@ -802,7 +805,8 @@ extern "C" int pk_eval_hessian(pk_engine* e, const double* x, const double* lam,
 // (Ipopt asks for f, grad f, g, J and H at the same x; ipopt.py:41-53).
 extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, const double* sig, const int* modes,
                            int n_modes, double* const* outs) {
-  if (!e || !x || !modes || !outs || n_modes < 1) return fail("pk_eval_set: bad argument");
+  if (!e || !modes || !outs || n_modes < 1) return fail("pk_eval_set: bad argument");
+  if (!x && !e->x_resident) return fail("pk_eval_set: x = NULL reuses the resident point, but none was uploaded yet");
   CK(cudaSetDevice(e->device));
   bool hess = false;
   for (int k = 0; k < n_modes; ++k) {
@@ -813,7 +817,7 @@ extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, con
     hess = hess || modes[k] == PK_MODE_HESSIAN;
   }
   if (hess && (!lam || !sig)) return fail("pk_eval_set: multipliers required for the Hessian");
-  if (pk_upload_x(e, x)) return 1;
+  if (x && pk_upload_x(e, x)) return 1;
   if (hess && pk_upload_multipliers(e, lam, sig)) return 1;
   if (use_pipeline(e, modes, n_modes)) {
     // one pipeline for all five; the copies of its slices follow on the same stream, largest first
@@ -1027,6 +1031,19 @@ extern "C" int pk_timeline(pk_engine* e, const int* modes, int n_modes, double* 
   *n_rows = n;
   cudaEventDestroy(base);
   cudaEventDestroy(end);
+  return 0;
+}
+
+extern "C" int pk_x_uploads(pk_engine* e, int64_t* count) {
+  if (!e || !count) return fail("pk_x_uploads: null argument");
+  *count = e->x_uploads;
+  return 0;
+}
+
+extern "C" int pk_expand_variant(pk_engine* e, int mode, int* variant) {
+  if (!e || !variant || mode < 0 || mode >= PK_N_MODES) return fail("pk_expand_variant: bad argument");
+  const ModeState& ms = e->mode[mode];
+  *variant = ms.exp.empty() ? 0 : (ms.exp.back().cols ? 2 : 1);
   return 0;
 }
 

@@ -96,6 +96,8 @@ def load_library():
         "pk_time": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
         "pk_time_steps": ([vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "pk_kernel_launches": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "pk_expand_variant": ([vp, C.c_int, C.POINTER(C.c_int)], C.c_int),
+        "pk_x_uploads": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "pk_timeline": ([vp, C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.POINTER(C.c_int)], C.c_int),
         "pk_flush_l2": ([vp], C.c_int),
         "pk_alloc_host": ([C.c_size_t], vp),
@@ -318,7 +320,7 @@ class Engine:
             modes = [P.OBJ, P.GRAD, P.CONS, P.JAC] + ([P.HESS] if fct_c is not None else [])
         modes = list(modes)
         self._load_for_set(modes)
-        x = self._x(x)
+        x = None if x is None else self._x(x)  # None: evaluate at the point already resident on the device
         lam = sig = None
         if P.HESS in modes:
             if fct_c is None:
@@ -330,7 +332,7 @@ class Engine:
         bufs = [self._out(m, None if outs is None else outs[k]) for k, m in enumerate(modes)]
         marr = (C.c_int * len(modes))(*modes)
         parr = (C.c_void_p * len(modes))(*[b.ctypes.data for b in bufs])
-        self._check(self.lib.pk_eval_set(self._h, _ptr(x), None if lam is None else _ptr(lam),
+        self._check(self.lib.pk_eval_set(self._h, None if x is None else _ptr(x), None if lam is None else _ptr(lam),
                                          None if sig is None else _ptr(sig), marr, len(modes), parr))
         res = {}
         for m, b in zip(modes, bufs):
@@ -437,8 +439,21 @@ class Engine:
         self._check(self.lib.pk_timeline(self._h, arr, len(modes), _ptr(rows), 256, C.byref(n)))
         return [(int(r[0]), int(r[1]), int(r[2]), float(r[3])) for r in rows[: n.value]]
 
+    def expand_kernel(self, mode: int) -> str:
+        """Name of the block-expansion kernel ``mode`` launches ('' if it has none)."""
+        self.load(mode)
+        v = C.c_int()
+        self._check(self.lib.pk_expand_variant(self._h, mode, C.byref(v)))
+        return {0: "", 1: "pk_expand_blocks", 2: "pk_expand_cols"}[v.value]
+
     def flush_l2(self):
         self._check(self.lib.pk_flush_l2(self._h))
+
+    @property
+    def x_uploads(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.pk_x_uploads(self._h, C.byref(n)))
+        return n.value
 
     @property
     def launches(self) -> int:

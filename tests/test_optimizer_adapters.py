@@ -1,0 +1,127 @@
+"""CPU tier: the solver adapters' host logic -- guess packing (reference behaviour and error texts,
+pockit/optimizer/_common.py:9-63) and the x-keyed evaluation cache, with the host-emulated plan
+standing in for the CUDA engine."""
+import numpy as np
+import pytest
+
+from helpers import build, load
+from hostemu import HostEmu
+from pockit_b200 import plan as P
+from pockit_b200.optimizer._cache import CachedCallbacks
+from pockit_b200.optimizer._common import pack_guess, unpack_solution
+
+
+class EmuEngine:
+    """Engine.evaluate() stand-in (test infrastructure): records what was asked for."""
+
+    def __init__(self, S):
+        self.e = HostEmu(S)
+        self.lowering = S.lowering
+        self.compacted = set()
+        self.calls = []
+        self.x = None
+
+    def evaluate(self, x, fct_c=None, fct_o=None, modes=None, outs=None):
+        self.calls.append((x is not None, tuple(modes)))
+        if x is not None:
+            self.x = np.array(x, copy=True)
+        res = {}
+        for m in modes:
+            v = self.e.run(m, self.x, fct_c, None if fct_o is None else float(np.asarray(fct_o).reshape(-1)[0]))
+            res[m] = v[0] if m == P.OBJ else v
+        return res
+
+
+class FakeSystem:
+    def __init__(self, S):
+        self._S = S
+        self.engine = EmuEngine(S)
+
+    def __getattr__(self, k):
+        return getattr(self._S, k)
+
+
+def test_cache_groups_callbacks_and_uploads_once_per_point():
+    S, g = build("robot_arm_lgr_6x20"), load("robot_arm_lgr_6x20")
+    F = FakeSystem(S)
+    cb = CachedCallbacks(F)
+    x, lam, sigma = g["x"], g["lam"], float(g["sigma"])
+    f = cb.objective(x)
+    c = cb.constraints(x.copy())          # same point, different array object: served from the cache
+    gr = cb.gradient(x)
+    J = cb.jacobian(x)
+    H = cb.hessian(x, lam, sigma)
+    np.testing.assert_allclose(f, g["objective"], rtol=1e-12)
+    np.testing.assert_allclose(c, g["constraints"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(gr, g["gradient"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(J, g["jacobian"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(H, g["hessian"], rtol=1e-12, atol=1e-14)
+    # three engine calls for five callbacks, x sent with the first one only
+    assert F.engine.calls == [(True, (P.OBJ, P.CONS)), (False, (P.GRAD, P.JAC)), (False, (P.HESS,))]
+    assert cb.stats == {"points": 1, "engine_calls": 3, "hits": 2}
+    # a line-search trial point: new upload, only the {f, g} group
+    x2 = x + 1e-3
+    cb.objective(x2); cb.constraints(x2)
+    assert F.engine.calls[-1] == (True, (P.OBJ, P.CONS)) and len(F.engine.calls) == 4
+    # back to the first point: the cache holds one point, so it is evaluated again
+    cb.jacobian(x)
+    assert F.engine.calls[-1] == (True, (P.GRAD, P.JAC))
+    # SciPy's split Hessians
+    n_o = S.lowering.nnz_hess_o
+    np.testing.assert_allclose(cb.hessian_o(x), g["hessian_o"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(cb.hessian_c(x, lam), g["hessian"][n_o:], rtol=1e-12, atol=1e-14)
+    # attribute passthrough (bounds / structures are the system's own)
+    assert cb.L == S.L and np.array_equal(cb.jacobianstructure()[0], S.jacobianstructure()[0])
+
+
+def test_cache_without_grouping_and_nan_points():
+    S, g = build("lqr_lgl_10x10"), load("lqr_lgl_10x10")
+    F = FakeSystem(S)
+    cb = CachedCallbacks(F, grouping=False)
+    x = g["x"]
+    cb.objective(x); cb.constraints(x)
+    assert F.engine.calls == [(True, (P.OBJ,)), (False, (P.CONS,))]
+    xn = x.copy(); xn[3] = np.nan
+    cb.objective(xn); cb.objective(xn)     # NaN never equals itself: evaluated twice, never served stale
+    assert [c[0] for c in F.engine.calls[-2:]] == [True, True]
+
+
+def test_guess_packing_follows_the_reference():
+    import pockit_b200.lobatto as lob
+    from pockit_b200 import problems
+    from pockit_b200.guess import linear_guess
+
+    S = problems.rocket(lob, mesh=4, num_point=5)
+    guesses = [linear_guess(p, 0.5) for p in S.p]
+    s0 = np.linspace(1.0, 2.0, S.n_s)
+    x0, single, opts = pack_guess(S, guesses + [s0], None)
+    assert not single and opts == {} and len(x0) == S.L
+    for i, gq in enumerate(guesses):
+        assert np.array_equal(x0[S.l_p[i] : S.r_p[i]], gq.data)
+    assert np.array_equal(x0[S.l_s : S.r_s], s0)
+    with pytest.raises(ValueError, match="number of phases \\+ 1"):
+        pack_guess(S, guesses, None)
+    back = unpack_solution(S, x0, False)
+    assert len(back) == S.n_p + 1 and np.array_equal(back[-1], s0)
+    # boundary slots come back substituted (FIXED / FUNC values), everything else untouched
+    p = S.p[0]
+    for j in range(p.n_x):
+        assert back[0].data[p.l_v[j]] == p._value_boundary_condition(p.info_bc_0[j], x0[S.l_p[0] + p.l_v[j]], s0)
+    L = problems.lqr(lob, 3, 3)
+    gq = linear_guess(L.p[0], 0.5) if not L.n_s else None
+    if gq is not None:
+        x0, single, _ = pack_guess(L, gq, {"maxiter": 3})
+        assert single and isinstance(unpack_solution(L, x0, True), type(gq))
+
+
+def test_ipopt_adapter_needs_cyipopt():
+    import importlib.util
+
+    import pockit_b200.lobatto as lob
+    from pockit_b200 import problems
+    from pockit_b200.optimizer import ipopt
+
+    if importlib.util.find_spec("cyipopt") is not None:
+        pytest.skip("cyipopt is installed here")
+    with pytest.raises(ImportError, match="cyipopt"):
+        ipopt.solve(problems.lqr(lob, 3, 3), None)
