@@ -50,6 +50,7 @@ struct ModeState {
   cudaKernel_t sys_kernel = nullptr;
   long long n_scalar = 0, n_out = 0;
   double* OUT = nullptr;  // [B][n_out], owned by the mode so that a full evaluation set stays resident
+  double* OUT_alloc = nullptr;  // the allocation; OUT starts 0..3 doubles into it (see load_mode)
   double *S = nullptr, *W = nullptr;  // scalar / node tables of this mode (modes may run concurrently)
   cudaStream_t stream = nullptr;      // used when a whole evaluation set is launched at once
   cudaEvent_t done = nullptr;
@@ -190,7 +191,7 @@ static void free_mode(ModeState& ms) {
   for (auto& g : ms.exp)
     if (g.prefix) cudaFree(g.prefix);
   if (ms.lib) cudaLibraryUnload(ms.lib);
-  if (ms.OUT) cudaFree(ms.OUT);
+  if (ms.OUT_alloc) cudaFree(ms.OUT_alloc);
   if (ms.S) cudaFree(ms.S);
   if (ms.W) cudaFree(ms.W);
   if (ms.stream) cudaStreamDestroy(ms.stream);
@@ -407,7 +408,26 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     if (ms.sub_off[k] < 0 || ms.sub_cnt[k] < 0 || ms.sub_off[k] + ms.sub_cnt[k] > d->n_out) return fail("pk_engine_load_mode: callback range outside the output");
   }
   for (auto& other : e->mode) other.in_set = false;
-  CK(cudaMalloc((void**)&ms.OUT, sizeof(double) * (size_t)e->dims.batch * (size_t)(d->n_out > 0 ? d->n_out : 1)));
+  {
+    // The reference's slot offsets are only 8-byte aligned, but the block expansion writes most of
+    // the bytes: start the output 0..3 doubles into its allocation so that the offset shared by most
+    // expanded lists falls on a 32-byte sector boundary (robot_arm LGR 2000x20: all 15 Jacobian lists
+    // start at 2 mod 4 -> 10.4 sectors per store request become 8).
+    long long votes[4] = {0, 0, 0, 0};
+    const pk_job* ej = d->jobs[PK_STAGE_EXPAND];
+    for (long long j = 0; j < d->n_jobs[PK_STAGE_EXPAND]; ++j)
+      for (long long l = 0; l < ej[j].i[1]; ++l) {
+        const size_t at = (size_t)(ej[j].i[0] + 2 * l);
+        if (at < e->h_ipool.size()) votes[e->h_ipool[at] & 3] += ej[j].i[11] * ej[j].i[4];
+      }
+    int best = 0;
+    for (int k = 1; k < 4; ++k)
+      if (votes[k] > votes[best]) best = k;
+    const char* env = getenv("POCKIT_B200_ALIGN");
+    const int shift = (env && env[0] == '0') ? 0 : (4 - best) & 3;
+    CK(cudaMalloc((void**)&ms.OUT_alloc, sizeof(double) * ((size_t)e->dims.batch * (size_t)(d->n_out > 0 ? d->n_out : 1) + 4)));
+    ms.OUT = ms.OUT_alloc + shift;
+  }
   {
     const size_t ns = sizeof(double) * (size_t)e->dims.batch * (size_t)(d->n_scalar > 0 ? d->n_scalar : 1);
     const size_t nw = sizeof(double) * (size_t)(e->dims.n_table > 0 ? e->dims.n_table : 1);
@@ -942,6 +962,35 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
     }
     e->set_launches = e->launches - before;
     e->launches = before;
+    // Priorities inside the graph: every kernel except the block expansions is latency-bound and
+    // small; give those nodes the highest priority so that their few blocks are dispatched as soon as
+    // an expansion block retires instead of queueing behind the thousands still pending.
+    {
+      const char* pe = getenv("POCKIT_B200_GRAPH_PRIORITY");
+      int prio_lo = 0, prio_hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      if (!(pe && pe[0] == '0') && prio_hi != prio_lo) {
+        size_t n_nodes = 0;
+        CK(cudaGraphGetNodes(graph, nullptr, &n_nodes));
+        std::vector<cudaGraphNode_t> nodes(n_nodes);
+        if (n_nodes) CK(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
+        const void* big[] = {(const void*)pk_expand_cols<true>, (const void*)pk_expand_cols<false>, (const void*)pk_expand_blocks};
+        for (cudaGraphNode_t nd : nodes) {
+          cudaGraphNodeType ty;
+          if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+          cudaKernelNodeParams kp;
+          bool is_big = false;
+          if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess)
+            for (const void* f : big) is_big = is_big || kp.func == f;
+          else
+            (void)cudaGetLastError();  // library (NVRTC) kernels: not a host function pointer -- small by construction
+          cudaLaunchAttributeValue v;
+          memset(&v, 0, sizeof(v));
+          v.priority = is_big ? prio_lo : prio_hi;
+          if (cudaGraphKernelNodeSetAttribute(nd, cudaLaunchAttributePriority, &v) != cudaSuccess) (void)cudaGetLastError();
+        }
+      }
+    }
     CK(cudaGraphInstantiate(&e->set_graph, graph, 0));
     cudaGraphDestroy(graph);
     e->set_modes = want;
