@@ -46,10 +46,21 @@ sys.path.insert(0, str(ROOT))
 METRIC = "NLP callback eval-sets/s (objective+gradient+constraints+Jacobian+Hessian) at 40k nodes"
 UNIT = "eval-sets/s"
 WORKLOAD = dict(builder="robot_arm", scheme="radau", mesh=2000, num_point=20)
+_NAME = "robot_arm LGR 2000x20 (40000 nodes; BASELINE.json configs[1])"
+# the other BASELINE.json configurations: only the CPU arm can be pointed at them
+# (`bench.py --impl reference --workload humanoid`), so that tools/measure_configs.py gets its CPU
+# column from this file's cpu leg instead of touching oracle/ itself
+OTHER_WORKLOADS = {
+    "lqr": (dict(builder="lqr", scheme="lobatto", mesh=10, num_point=10), "LQR LGL 10x10 (BASELINE.json configs[0])"),
+    "humanoid": (dict(builder="humanoid", scheme="lobatto", mesh=11112, num_point=10), "humanoid LGL 11112x10 (configs[2])"),
+    "humanoid_small": (dict(builder="humanoid", scheme="lobatto", mesh=1000, num_point=10), "humanoid LGL 1000x10 (configs[2])"),
+    "rocket": (dict(builder="rocket", scheme="lobatto", mesh=5556, num_point=10), "two-stage rocket LGL 2x5556x10 (configs[3])"),
+    "quadrotor": (dict(builder="quadrotor", scheme="lobatto", mesh=14, num_point=6), "quadrotor LGL 14x6, one instance (configs[4])"),
+}
 
 
 def workload_name():
-    return "robot_arm LGR 2000x20 (40000 nodes; BASELINE.json configs[1])"
+    return _NAME
 
 
 def build_system(seed_shift: int = 0):
@@ -152,9 +163,14 @@ def cpu_eval_sets_per_s(workers: int, sets: int):
 
 
 def run_reference(args, rank, world):
+    global _NAME
     if rank != 0:
         return
-    cores = max(1, min(os.cpu_count() or 1, 8))
+    if args.workload != "robot_arm":
+        wl, _NAME = OTHER_WORKLOADS[args.workload]
+        WORKLOAD.clear()
+        WORKLOAD.update(wl)
+    cores = args.cores or max(1, min(os.cpu_count() or 1, 8))
     sets = max(1, min(args.steps, 5))  # bounded sample: ~1 s per set and worker
     value, worst = cpu_eval_sets_per_s(cores, sets)
     line = {
@@ -179,6 +195,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="robot_arm", choices=["robot_arm"] + sorted(OTHER_WORKLOADS),
+                    help="CPU arm only (--impl reference): time another BASELINE.json configuration")
+    ap.add_argument("--cores", type=int, default=0, help="CPU arm only: worker processes (default: min(8, host cores))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-compact", action="store_true", help="skip the extra de-duplicated-pattern measurement")
     args = ap.parse_args()
@@ -189,6 +208,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.workload != "robot_arm":
+        raise SystemExit("bench.py: --workload selects the CPU arm's configuration only; the GPU arm measures BASELINE.json configs[1]")
 
     import torch
 

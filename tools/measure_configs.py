@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Measure the five BASELINE.json configurations on one GPU (plus the CPU oracle on a
-bounded sample) and print one JSON line per configuration.  Not the bench contract --
+"""Measure the five BASELINE.json configurations on one GPU (plus, through bench.py's CPU arm, the
+CPU port on a bounded sample) and print one JSON line per configuration.  Not the bench contract --
 bench.py is -- this fills the table in DESIGN.md / README.md.
 
     python tools/measure_configs.py [--skip-cpu] [name ...]
@@ -24,6 +24,12 @@ CONFIGS = {
     "C3_humanoid_lgl_11112x10": ("humanoid", "lobatto", dict(mesh=11112, num_point=10), 1),
     "C4_rocket_lgl_2x5556x10": ("rocket", "lobatto", dict(mesh=5556, num_point=10), 1),
     "C5_quadrotor_lgl_14x6_B8192": ("quadrotor", "lobatto", dict(mesh=14, num_point=6), 8192),
+}
+
+
+CPU_WORKLOAD = {
+    "C1_lqr_lgl_10x10": "lqr", "C2_robot_arm_lgr_2000x20": "robot_arm", "C3_humanoid_lgl_1000x10": "humanoid_small",
+    "C3_humanoid_lgl_11112x10": "humanoid", "C4_rocket_lgl_2x5556x10": "rocket", "C5_quadrotor_lgl_14x6_B8192": "quadrotor",
 }
 
 
@@ -102,19 +108,14 @@ def main():
             for mname, mm in zip(P.MODES, range(5)):
                 tot, st = eng.time(mm, iters=10, stages=True)
                 line["ms_per_callback"][mname] = dict(total=tot / 10, **{k: v / 10 for k, v in zip(names, st) if v > 0})
-        if not args.skip_cpu:
-            from oracle.pockit_oracle import OracleSystem
+        if not args.skip_cpu and name in CPU_WORKLOAD:
+            # the CPU column comes from bench.py's cpu leg (the only non-test code that runs oracle/)
+            import subprocess
 
-            O = OracleSystem(S)
-            xs = X if B == 1 else X[0]
-            ls = LAM if B == 1 else LAM[0]
-            def cpu_set():
-                O.objective(xs); O.gradient(xs); O.constraints(xs); O.jacobian(xs); O.hessian(xs, ls, sigma)
-            cpu_set()
-            n_cpu, t0 = 0, time.perf_counter()
-            while n_cpu < 3 or (time.perf_counter() - t0 < 3.0 and n_cpu < 200):
-                cpu_set(); n_cpu += 1
-            line["cpu_port_sets_per_s_1core"] = n_cpu / (time.perf_counter() - t0)
+            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", CPU_WORKLOAD[name],
+                                "--cores", "1", "--steps", "3", "--warmup", "1"], capture_output=True, text=True)
+            if r.returncode == 0 and r.stdout.strip():
+                line["cpu_port_sets_per_s_1core"] = json.loads(r.stdout.strip().splitlines()[-1])["value"]
         print(json.dumps(line), flush=True)
         eng.close()
 
