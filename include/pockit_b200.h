@@ -164,6 +164,27 @@ int pk_engine_set_output_runs(pk_engine *e, int mode, const int64_t *runs, int64
 int pk_engine_set_compaction(pk_engine *e, int mode, int64_t n_unique, const int64_t *seg_ptr, const int64_t *perm);
 int pk_out_size(pk_engine *e, int mode, int64_t *n); /* values per instance the host receives for this mode */
 
+/* ---- continuous error-estimate data on the augmented mesh (the next host hot spot of an hp-adaptive
+ * loop; PhaseBase._error_estimation_data_continuous, phasebase.py:1355-1366) ----
+ * Per phase: xs = x with boundary values substituted (generated `prep` program), xu_aug = V.xs,
+ * f_i at the augmented nodes (generated `node` program), T_x_aug = T.xs, I_f_aug = dt * (I.f_i).
+ * The three operators are CSR matrices applied with sequential row sums, like the reference's csr.dot.
+ * Engines with batch == 1 only. */
+typedef struct {
+  const char *prep_kernel, *node_kernel; /* NVRTC kernel names */
+  int64_t x_offset;                      /* first entry of the phase in x (l_p) */
+  int64_t L, L_xu, L_x_all;              /* phase vector length; state+control slots; state slots */
+  int64_t n_x, n_u, Lm_aug, rows;        /* augmented nodes; rows per state of T.x and I.f */
+  const double *tm_aug;                  /* [Lm_aug] mesh fractions of the augmented nodes */
+  const int64_t *V_ptr, *V_idx; const double *V_val; /* ((n_x+n_u)*Lm_aug) x L_xu */
+  const int64_t *T_ptr, *T_idx; const double *T_val; /* (n_x*rows) x L_x_all */
+  const int64_t *I_ptr, *I_idx; const double *I_val; /* rows x Lm_aug */
+} pk_aug_phase;
+int pk_engine_load_error_estimate(pk_engine *e, const char *cuda_source, const char *const *nvrtc_options,
+                                  int n_nvrtc_options, const pk_aug_phase *phases, int n_phases);
+/* t_x / i_f: phases concatenated, each [n_x][rows] */
+int pk_eval_error_data(pk_engine *e, const double *x, double *t_x, double *i_f);
+
 /* ---- device-resident path (inputs already in HBM): upload once, run many, download ---- */
 int pk_upload_x(pk_engine *e, const double *x);
 int pk_upload_multipliers(pk_engine *e, const double *lambda, const double *sigma);
@@ -185,8 +206,9 @@ int pk_time_steps(pk_engine *e, const int *modes, int n_modes, int steps, int fl
  * rows[4*i..] = (mode, tag, edge, microseconds); tag = job stage 0..5, 6 node programs, 7 system
  * program, 8 compaction; edge 0 = before, 1 = after; the last row (mode -1) is the whole set */
 int pk_timeline(pk_engine *e, const int *modes, int n_modes, double *rows, int max_rows, int *n_rows);
-/* which block-expansion kernel a loaded mode uses: 0 none, 1 pk_expand_blocks (persistent column
- * walk, any mix of orders), 2 pk_expand_cols (parameter-driven column walk, same-order meshes) */
+/* which block-expansion kernel a loaded mode uses: 0 none, 1 the persistent column walk for any
+ * mix of orders [kernel pk_expand_blocks], 2 the parameter-driven column walk for same-order
+ * meshes [kernel pk_expand_cols] */
 int pk_expand_variant(pk_engine *e, int mode, int *variant);
 int pk_kernel_launches(pk_engine *e, int64_t *count);
 int pk_x_uploads(pk_engine *e, int64_t *count);       /* host-to-device copies of x so far */ /* kernels launched so far by this engine */

@@ -468,6 +468,23 @@ class OPhase:
             out.append(tx - self.I_csr.dot(self.F_d[i].F(vb, self.L_m)) * dt)
         return _cat(out)
 
+    def error_estimation_data_continuous(self, x, s):  # :1339-1366
+        """``(T_x_aug . x, dt * I_m_aug . f(V_xu_aug . x))`` on the augmented mesh, each ``[n_x][rows]``."""
+        from pockit_b200.discretization import AugmentedCollocation
+
+        if not hasattr(self, "_aug"):
+            self._aug = AugmentedCollocation(self.col)
+        A, col = self._aug, self.col
+        _, dt, xs = self.value_basic(x, s)  # boundary values substituted first (:1340-1347)
+        mt = (xs[-1] + xs[-2]) / 2
+        t_aug = (A.t_m - 0.5) * dt + mt
+        xu_aug = A.V.dot(xs[: col.L_xu])
+        vb_aug = np.concatenate([xu_aug, t_aug, np.repeat(s, A.L_m)])
+        L_x_all = col.r_v[self.n_x - 1] if self.n_x else 0
+        T_x = A.T.dot(xs[:L_x_all]).reshape(self.n_x, -1)
+        I_f = np.array([A.I.dot(f.F(vb_aug, A.L_m)) for f in self.F_d]).reshape(self.n_x, -1) * dt
+        return T_x, I_f
+
     def value_path(self, x, s):  # :1014-1021
         vb, _, _ = self.value_basic(x, s)
         return _cat([f.F(vb, self.L_m) for f in self.F_c])
@@ -678,6 +695,11 @@ class OracleSystem:
             k += p.n_I
         v[k:] = s
         return v
+
+    def error_estimation_data(self, x):
+        """Per phase ``(T_x_aug, I_f_aug)`` (``phasebase.py:1355-1366``)."""
+        s, xs = self._split(x)
+        return [p.error_estimation_data_continuous(x_, s) for p, x_ in zip(self.p, xs)]
 
     def objective(self, x):  # :602-605
         return self.F_o.F(self._value_basic(self.which_o, x), 1)[0]

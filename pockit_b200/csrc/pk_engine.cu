@@ -92,6 +92,16 @@ struct pk_engine {
   double* flush = nullptr; long long n_flush = 0;
   long long n_out_max = 0;
   ModeState mode[PK_N_MODES];
+  struct AugPhase {
+    cudaKernel_t prep = nullptr, node = nullptr;
+    long long x_offset = 0, L = 0, L_xu = 0, L_x_all = 0, n_x = 0, n_u = 0, Lm_aug = 0, rows = 0;
+    double *tm = nullptr, *XS = nullptr, *XU = nullptr, *WA = nullptr, *TX = nullptr, *IF = nullptr;
+    long long *Vp = nullptr, *Vi = nullptr, *Tp = nullptr, *Ti = nullptr, *Ip = nullptr, *Ii = nullptr;
+    double *Vv = nullptr, *Tv = nullptr, *Iv = nullptr;
+  };
+  std::vector<AugPhase> aug;  // continuous error estimate (pk_engine_load_error_estimate)
+  cudaLibrary_t aug_lib = nullptr;
+  std::vector<char> aug_cubin;
   long long launches = 0, set_launches = 0, x_uploads = 0;
   bool x_resident = false;
   // pk_timeline: timing events around every launch of a set
@@ -207,10 +217,22 @@ static void free_mode(ModeState& ms) {
   ms = ModeState();
 }
 
+static void free_aug(pk_engine* e) {
+  for (auto& a : e->aug) {
+    void* ptrs[] = {a.tm, a.XS, a.XU, a.WA, a.TX, a.IF, a.Vp, a.Vi, a.Tp, a.Ti, a.Ip, a.Ii, a.Vv, a.Tv, a.Iv};
+    for (void* q : ptrs)
+      if (q) cudaFree(q);
+  }
+  e->aug.clear();
+  if (e->aug_lib) cudaLibraryUnload(e->aug_lib);
+  e->aug_lib = nullptr;
+}
+
 extern "C" int pk_engine_destroy(pk_engine* e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  free_aug(e);
   for (auto& ms : e->mode) free_mode(ms);
   cudaFree(e->X); cudaFree(e->LAM); cudaFree(e->SIG);
   if (e->set_graph) cudaGraphExecDestroy(e->set_graph);
@@ -247,9 +269,14 @@ extern "C" int pk_engine_set_fixed(pk_engine* e, const double* v) {
   return 0;
 }
 
+static int compile_source(const char* source, const char* const* extra, int n_extra, int device, std::vector<char>& cubin);
 static int compile(const pk_mode_desc* d, int device, std::vector<char>& cubin) {
+  return compile_source(d->cuda_source, d->nvrtc_options, d->n_nvrtc_options, device, cubin);
+}
+
+static int compile_source(const char* source, const char* const* extra, int n_extra, int device, std::vector<char>& cubin) {
   nvrtcProgram prog;
-  if (nvrtcCreateProgram(&prog, d->cuda_source, "pockit_b200_generated.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+  if (nvrtcCreateProgram(&prog, source, "pockit_b200_generated.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
     return fail("nvrtcCreateProgram failed");
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
@@ -258,9 +285,9 @@ static int compile(const pk_mode_desc* d, int device, std::vector<char>& cubin) 
                      ((prop.major == 10 && prop.minor == 0) ? "a" : "");
   std::vector<const char*> opts = {arch.c_str(), "--std=c++17", "-lineinfo"};
   bool fmad_given = false;  // strict IEEE products by default; a fastmath model passes --fmad=true
-  for (int i = 0; i < d->n_nvrtc_options; ++i) {
-    if (strncmp(d->nvrtc_options[i], "--fmad", 6) == 0 || strncmp(d->nvrtc_options[i], "-fmad", 5) == 0) fmad_given = true;
-    opts.push_back(d->nvrtc_options[i]);
+  for (int i = 0; i < n_extra; ++i) {
+    if (strncmp(extra[i], "--fmad", 6) == 0 || strncmp(extra[i], "-fmad", 5) == 0) fmad_given = true;
+    opts.push_back(extra[i]);
   }
   if (!fmad_given) opts.push_back("--fmad=false");
   nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
@@ -1080,6 +1107,85 @@ extern "C" int pk_timeline(pk_engine* e, const int* modes, int n_modes, double* 
   *n_rows = n;
   cudaEventDestroy(base);
   cudaEventDestroy(end);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// continuous error-estimate data (phasebase.py:1339-1366)
+template <typename T>
+static int to_device(T** dst, const T* src, size_t n) {
+  CK(cudaMalloc((void**)dst, sizeof(T) * (n ? n : 1)));
+  if (n) CK(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int pk_engine_load_error_estimate(pk_engine* e, const char* source, const char* const* opts, int n_opts,
+                                             const pk_aug_phase* phases, int n_phases) {
+  if (!e || !source || !phases || n_phases < 1) return fail("pk_engine_load_error_estimate: bad argument");
+  if (e->dims.batch != 1) return fail("pk_engine_load_error_estimate: engines with batch == 1 only");
+  CK(cudaSetDevice(e->device));
+  free_aug(e);
+  if (compile_source(source, opts, n_opts, e->device, e->aug_cubin)) return 1;
+  CK(cudaLibraryLoadData(&e->aug_lib, e->aug_cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  e->aug.resize(n_phases);
+  for (int i = 0; i < n_phases; ++i) {
+    const pk_aug_phase& p = phases[i];
+    pk_engine::AugPhase& a = e->aug[i];
+    if (p.x_offset < 0 || p.x_offset + p.L > e->dims.L || p.L_xu > p.L || p.L_x_all > p.L_xu)
+      return fail("pk_engine_load_error_estimate: phase layout outside x");
+    CK(cudaLibraryGetKernel(&a.prep, e->aug_lib, p.prep_kernel));
+    CK(cudaLibraryGetKernel(&a.node, e->aug_lib, p.node_kernel));
+    a.x_offset = p.x_offset; a.L = p.L; a.L_xu = p.L_xu; a.L_x_all = p.L_x_all;
+    a.n_x = p.n_x; a.n_u = p.n_u; a.Lm_aug = p.Lm_aug; a.rows = p.rows;
+    const size_t nv = (size_t)((p.n_x + p.n_u) * p.Lm_aug), nt = (size_t)(p.n_x * p.rows), ni = (size_t)p.rows;
+    if (to_device(&a.tm, p.tm_aug, (size_t)p.Lm_aug)) return 1;
+    if (to_device(&a.Vp, (const long long*)p.V_ptr, nv + 1) || to_device(&a.Vi, (const long long*)p.V_idx, (size_t)p.V_ptr[nv]) ||
+        to_device(&a.Vv, p.V_val, (size_t)p.V_ptr[nv])) return 1;
+    if (to_device(&a.Tp, (const long long*)p.T_ptr, nt + 1) || to_device(&a.Ti, (const long long*)p.T_idx, (size_t)p.T_ptr[nt]) ||
+        to_device(&a.Tv, p.T_val, (size_t)p.T_ptr[nt])) return 1;
+    if (to_device(&a.Ip, (const long long*)p.I_ptr, ni + 1) || to_device(&a.Ii, (const long long*)p.I_idx, (size_t)p.I_ptr[ni]) ||
+        to_device(&a.Iv, p.I_val, (size_t)p.I_ptr[ni])) return 1;
+    CK(cudaMalloc((void**)&a.XS, sizeof(double) * (size_t)(p.L > 0 ? p.L : 1)));
+    CK(cudaMalloc((void**)&a.XU, sizeof(double) * (nv ? nv : 1)));
+    CK(cudaMalloc((void**)&a.WA, sizeof(double) * (size_t)(p.n_x * p.Lm_aug > 0 ? p.n_x * p.Lm_aug : 1)));
+    CK(cudaMalloc((void**)&a.TX, sizeof(double) * (nt ? nt : 1)));
+    CK(cudaMalloc((void**)&a.IF, sizeof(double) * (nt ? nt : 1)));
+  }
+  return 0;
+}
+
+extern "C" int pk_eval_error_data(pk_engine* e, const double* x, double* t_x, double* i_f) {
+  if (!e || !x || !t_x || !i_f) return fail("pk_eval_error_data: null argument");
+  if (e->aug.empty()) return fail("pk_eval_error_data: pk_engine_load_error_estimate first");
+  CK(cudaSetDevice(e->device));
+  if (pk_upload_x(e, x)) return 1;
+  cudaStream_t st = e->stream;
+  size_t off = 0;
+  for (auto& a : e->aug) {
+    int B = 1;
+    {
+      void* args[] = {&e->X, &e->FIX, &a.XS, &B};
+      CK(cudaLaunchKernel((void*)a.prep, dim3(blocks_for(a.L, 128)), dim3(128), args, 0, st));
+    }
+    const long long nv = (a.n_x + a.n_u) * a.Lm_aug, nt = a.n_x * a.rows;
+    if (nv)
+      pk_csr_matvec<<<blocks_for(nv, PK_THREADS), PK_THREADS, 0, st>>>(a.Vp, a.Vi, a.Vv, a.XS, a.XU, nv, 0, 0, 1, nullptr, nullptr);
+    {
+      void* args[] = {&e->X, &a.XS, &a.XU, &a.tm, &a.WA, &B};
+      CK(cudaLaunchKernel((void*)a.node, dim3(blocks_for(a.Lm_aug, 128)), dim3(128), args, 0, st));
+    }
+    if (nt) {
+      pk_csr_matvec<<<blocks_for(nt, PK_THREADS), PK_THREADS, 0, st>>>(a.Tp, a.Ti, a.Tv, a.XS, a.TX, nt, 0, 0, 1, nullptr, nullptr);
+      pk_csr_matvec<<<blocks_for(nt, PK_THREADS), PK_THREADS, 0, st>>>(a.Ip, a.Ii, a.Iv, a.WA, a.IF, a.rows, a.Lm_aug, a.rows, (int)a.n_x,
+                                                                      a.XS + a.L - 1, a.XS + a.L - 2);
+      CK(cudaMemcpyAsync(t_x + off, a.TX, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(i_f + off, a.IF, sizeof(double) * (size_t)nt, cudaMemcpyDeviceToHost, st));
+    }
+    e->launches += 5;
+    off += (size_t)nt;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -478,6 +478,27 @@ __global__ void __launch_bounds__(PK_THREADS) pk_compact(const double* __restric
   OUTC[(long long)b * n_unique + u] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// CSR matrix-vector product with sequential row sums (the order of scipy.sparse csr_matvec):
+// y[g][r] = (sum_k val[k] * x[g][idx[k]]) [* (hi[0] - lo[0])] for g < groups.  Used by the continuous
+// error estimate (phasebase.py:1339-1366): interpolation to the augmented mesh, translation and
+// augmented integration are applied exactly like the reference's csr.dot.
+__global__ void __launch_bounds__(PK_THREADS) pk_csr_matvec(const long long* __restrict__ ptr, const long long* __restrict__ idx,
+                                                           const double* __restrict__ val, const double* __restrict__ x,
+                                                           double* __restrict__ y, long long n_rows, long long x_stride,
+                                                           long long y_stride, int groups, const double* __restrict__ hi,
+                                                           const double* __restrict__ lo) {
+  const long long gid = blockIdx.x * (long long)PK_THREADS + threadIdx.x;
+  if (gid >= n_rows * groups) return;
+  const int g = (int)(gid / n_rows);
+  const long long r = gid - (long long)g * n_rows;
+  const double* xv = x + (long long)g * x_stride;
+  double acc = 0.0;
+  for (long long k = ptr[r]; k < ptr[r + 1]; ++k) acc += val[k] * xv[idx[k]];
+  if (hi) acc = acc * (hi[0] - lo[0]);
+  y[(long long)g * y_stride + r] = acc;
+}
+
 // L2 flush helper for timing hygiene
 __global__ void pk_fill(double* p, long long n, double v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;

@@ -314,3 +314,106 @@ class Collocation:
     # node -> interval map, useful to the engine for non-uniform meshes
     def interval_of_row(self) -> np.ndarray:
         return np.repeat(np.arange(len(self.num_point)), np.diff(self.row_start))
+
+
+# ----------------------------------------------------------------------------
+# augmented mesh (one more point per interval): data of the continuous error estimate
+# ----------------------------------------------------------------------------
+@functools.lru_cache(maxsize=None)
+def _lagrange_values(nodes: tuple, at: tuple) -> np.ndarray:
+    """``V[k, i]`` = i-th Lagrange basis polynomial on ``nodes`` evaluated at ``at[k]``.
+
+    The reference builds these tables with ``scipy.interpolate.lagrange`` (monomial basis) and
+    ``numpy.polyval`` (``lobatto/discretization.py:256-301``, ``radau/discretization.py:286-355``);
+    that route is ill-conditioned at 20 points, so parity requires the same library calls."""
+    import warnings
+
+    import scipy.interpolate
+
+    nodes_a, at_a = np.array(nodes, dtype=np.float64), np.array(at, dtype=np.float64)
+    cols = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)  # SciPy deprecates `lagrange`; the reference uses it
+        for i in range(len(nodes_a)):
+            y = np.zeros(len(nodes_a))
+            y[i] = 1
+            cols.append(np.polyval(scipy.interpolate.lagrange(nodes_a, y), at_a))
+    return np.array(cols, dtype=np.float64).T
+
+
+class AugmentedCollocation:
+    """Operators of the continuous error estimate (``phasebase.py:1339-1366``) as CSR triplets:
+
+    * ``V``  interpolation of every state / control from the mesh to the augmented mesh
+      (``n_k + 1`` points per interval), block diagonal over the variables (``V_xu_aug``);
+    * ``T``  the same interpolant minus its value at the interval end (``T_x_aug``), states only;
+    * ``I``  the integration operator of the augmented mesh (``I_m(mesh, num_point + 1)``);
+    * ``t_m`` / ``l_m`` / ``r_m`` of the augmented mesh.
+
+    Every operator is applied as a CSR matrix-vector product with sequential row sums, exactly
+    like ``scipy.sparse.csr_array.dot`` in the reference."""
+
+    def __init__(self, col: Collocation):
+        import scipy.sparse as sp
+
+        self.col = col
+        scheme, mesh, npt = col.scheme, col.mesh, col.num_point.astype(np.int64)
+        aug = Collocation(scheme, mesh, npt + 1, col.n_x, col.n_u)
+        self.aug = aug
+        self.t_m, self.l_m, self.r_m, self.L_m = aug.t_m, aug.l_m, aug.r_m, aug.L_m
+        n_int = len(npt)
+        lgl = scheme == "lgl"
+        rule = gauss_lobatto if lgl else gauss_radau
+
+        def assemble(blocks, rows0, cols0, shape):
+            r, c, d = [], [], []
+            for blk, r0, c0 in zip(blocks, rows0, cols0):
+                nr, nc = blk.shape
+                r.append(r0 + np.repeat(np.arange(nr), nc))
+                c.append(c0 + np.tile(np.arange(nc), nr))
+                d.append(blk.ravel())
+            m = sp.coo_array((np.concatenate(d), (np.concatenate(r), np.concatenate(c))), shape=shape)
+            m.sum_duplicates()
+            m.eliminate_zeros()
+            return m.tocsr()
+
+        col0 = col.l_m  # first mesh node of every interval (LGL and LGR alike)
+        if lgl:
+            # rows: shared-border layout of the augmented mesh; the first row of every interval but
+            # the first is dropped (its value comes from the previous interval's last row)
+            vb, vr0, tb = [], [], []
+            for k in range(n_int):
+                n = int(npt[k])
+                x, xa = rule(n)[0], rule(n + 1)[0]
+                V = _lagrange_values(tuple(x), tuple(xa))            # (n+1) x n
+                vb.append(V if k == 0 else V[1:])
+                vr0.append(int(aug.l_m[k]) + (0 if k == 0 else 1))
+                tb.append(V[:-1] - V[-1])                             # n x n
+            Vs = assemble(vb, vr0, col0, (aug.L_m, col.L_m))
+            Vx = Vu = Vs
+            t_rows0 = np.concatenate(([0], np.cumsum(npt[:-1])))
+            Ts = assemble(tb, t_rows0, col0, (int(npt.sum()), col.L_m))
+        else:
+            vxb, vub, tb = [], [], []
+            for k in range(n_int):
+                n = int(npt[k])
+                x, xa = rule(n)[0], rule(n + 1)[0]
+                x1 = tuple(np.concatenate((x, [1.0])))
+                vxb.append(_lagrange_values(x1, tuple(xa)))           # (n+1) x (n+1), states carry the interval end
+                vub.append(_lagrange_values(tuple(x), tuple(xa)))     # (n+1) x n
+                Tv = _lagrange_values(x1, tuple(np.concatenate((xa, [1.0]))))
+                tb.append(Tv[:-1] - Tv[-1])                           # (n+1) x (n+1)
+            Vx = assemble(vxb, aug.l_m, col0, (aug.L_m, col.L_x))
+            Vu = assemble(vub, aug.l_m, col0, (aug.L_m, col.L_m))
+            Ts = assemble(tb, aug.l_m, col0, (aug.L_m, col.L_x))
+        self.V = sp.block_diag([Vx] * col.n_x + [Vu] * col.n_u).tocsr() if col.n_x + col.n_u else sp.csr_array((0, 0))
+        self.T = sp.block_diag([Ts] * col.n_x).tocsr() if col.n_x else sp.csr_array((0, 0))
+        self.rows = Ts.shape[0]  # rows per state of T.x and of I.f
+        I = aug.I
+        trip = [I.f, I.m, I.b]
+        Im = sp.coo_array((np.concatenate([t.data for t in trip]), (np.concatenate([t.row for t in trip]),
+                                                                   np.concatenate([t.col for t in trip]))),
+                          shape=(aug.n_rows, aug.L_m))
+        self.I = Im.tocsr()
+        self.I.sort_indices()
+        assert self.I.shape[0] == self.rows

@@ -49,6 +49,18 @@ class _ModeDesc(C.Structure):
     ]
 
 
+class _AugPhase(C.Structure):
+    _fields_ = [
+        ("prep_kernel", C.c_char_p), ("node_kernel", C.c_char_p), ("x_offset", C.c_int64),
+        ("L", C.c_int64), ("L_xu", C.c_int64), ("L_x_all", C.c_int64),
+        ("n_x", C.c_int64), ("n_u", C.c_int64), ("Lm_aug", C.c_int64), ("rows", C.c_int64),
+        ("tm_aug", C.c_void_p),
+        ("V_ptr", C.c_void_p), ("V_idx", C.c_void_p), ("V_val", C.c_void_p),
+        ("T_ptr", C.c_void_p), ("T_idx", C.c_void_p), ("T_val", C.c_void_p),
+        ("I_ptr", C.c_void_p), ("I_idx", C.c_void_p), ("I_val", C.c_void_p),
+    ]
+
+
 assert C.sizeof(_Job) == P.JOB_DTYPE.itemsize
 
 _LIB = None
@@ -87,6 +99,8 @@ def load_library():
         "pk_engine_set_output_runs": ([vp, C.c_int, vp, C.c_int64], C.c_int),
         "pk_engine_set_compaction": ([vp, C.c_int, C.c_int64, vp, vp], C.c_int),
         "pk_out_size": ([vp, C.c_int, C.POINTER(C.c_int64)], C.c_int),
+        "pk_engine_load_error_estimate": ([vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(_AugPhase), C.c_int], C.c_int),
+        "pk_eval_error_data": ([vp, vp, vp, vp], C.c_int),
         "pk_upload_x": ([vp, vp], C.c_int),
         "pk_upload_multipliers": ([vp, vp, vp], C.c_int),
         "pk_run": ([vp, C.c_int], C.c_int),
@@ -384,6 +398,47 @@ class Engine:
         if P.HESS in self.compacted:
             return np.array(full)
         return np.array(full[..., self.lowering.nnz_hess_o :])
+
+    # ------------------------------------------------------------------ continuous error estimate
+    def error_estimation_data(self, x):
+        """Per phase ``(T_x_aug, I_f_aug)``, each ``[n_x][rows]``: the data
+        ``PhaseBase._error_estimation_data_continuous`` (``phasebase.py:1355-1366``) hands to the
+        mesh-refinement checks, computed on the device (programs and operators: ``plan.error_estimate``)."""
+        if self.B != 1:
+            raise ValueError("error-estimate data is available for engines with batch == 1")
+        if getattr(self, "_aug", None) is None:
+            ee = self.plan.error_estimate()
+            keep, arr = [], (_AugPhase * len(ee["phases"]))()
+            for k, ph in enumerate(ee["phases"]):
+                a = arr[k]
+                a.prep_kernel, a.node_kernel = ph["prep"].encode(), ph["node"].encode()
+                for f in ("x_offset", "L", "L_xu", "L_x_all", "n_x", "n_u", "Lm_aug", "rows"):
+                    setattr(a, f, ph[f])
+                tm = np.ascontiguousarray(ph["tm_aug"], dtype=np.float64)
+                keep.append(tm)
+                a.tm_aug = tm.ctypes.data
+                for name in ("V", "T", "I"):
+                    m = ph[name].tocsr()
+                    m.sort_indices()
+                    ptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+                    idx = np.ascontiguousarray(m.indices, dtype=np.int64)
+                    val = np.ascontiguousarray(m.data, dtype=np.float64)
+                    keep += [ptr, idx, val]
+                    setattr(a, name + "_ptr", ptr.ctypes.data)
+                    setattr(a, name + "_idx", idx.ctypes.data)
+                    setattr(a, name + "_val", val.ctypes.data)
+            opts = (C.c_char_p * max(1, len(self._opts)))(*[o.encode() for o in self._opts])
+            self._check(self.lib.pk_engine_load_error_estimate(self._h, ee["source"].encode(), opts, len(self._opts), arr, len(ee["phases"])))
+            self._aug = [(ph["n_x"], ph["rows"]) for ph in ee["phases"]]
+        x = self._x(x)
+        n = sum(nx * rows for nx, rows in self._aug)
+        tx, jf = np.empty(max(n, 1)), np.empty(max(n, 1))
+        self._check(self.lib.pk_eval_error_data(self._h, _ptr(x), _ptr(tx), _ptr(jf)))
+        out, off = [], 0
+        for nx, rows in self._aug:
+            out.append((tx[off : off + nx * rows].reshape(nx, rows).copy(), jf[off : off + nx * rows].reshape(nx, rows).copy()))
+            off += nx * rows
+        return out
 
     # ------------------------------------------------------------------ device-resident path
     def upload(self, x, fct_c=None, fct_o=None):

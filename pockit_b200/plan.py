@@ -939,6 +939,93 @@ class DevicePlan:
         A("}")
         return "\n".join(L)
 
+    # ---------------------------------------------------------------- continuous error estimate
+    def error_estimate(self) -> dict:
+        """Programs and operators of the continuous error-estimate data (SURVEY 8f.3,
+        ``phasebase.py:1339-1366``): per phase a *prep* program (the phase vector with its FIXED /
+        FUNC boundary values substituted), a *node* program (the dynamics at the augmented-mesh
+        nodes, read from the interpolated states / controls) and the CSR operators ``V`` (mesh ->
+        augmented mesh), ``T`` (translation) and ``I`` (augmented integration) the engine applies
+        with sequential row sums, like the reference's ``csr.dot``."""
+        from .discretization import AugmentedCollocation
+
+        lo = self.lo
+        body, phases = [], []
+        for pi, p in enumerate(lo.phases):
+            col = p.col
+            A = AugmentedCollocation(col)
+            n_x, n_u = p.n_x, p.n_u
+            names = {}
+            L = []
+            add = L.append
+            prep, node = f"pk_aug_prep_p{pi}", f"pk_aug_node_p{pi}"
+            # --- prep: xs = phase slice of x with boundary values substituted (phasebase.py:1340-1347)
+            add(f'extern "C" __global__ void {prep}(const double* __restrict__ X, const double* __restrict__ FIX,')
+            add("    double* __restrict__ XS, int B)")
+            add("{")
+            add("    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;")
+            add(f"    if (gid >= (long long)B * {col.L}) return;")
+            add(f"    const int b = (int)(gid / {col.L});")
+            add(f"    const int k = (int)(gid - (long long)b * {col.L});")
+            add(f"    const double* xp = X + (long long)b * {lo.r_s} + {int(lo.l_p[pi])};")
+            add(f"    const double* sv = X + (long long)b * {lo.r_s} + {lo.l_s};")
+            add(f"    const double* fix = FIX + (long long)b * {self.n_fixed} + {self.fix_off[pi]};")
+            for k, sym in enumerate(p.s):
+                add(f"    const double s{k} = sv[{k}];")
+                names[sym] = f"s{k}"
+            infos = ([(("x0", i), p.info_bc_0[i], int(col.l_v[i]), i) for i in range(n_x)]
+                     + [(("xf", i), p.info_bc_f[i], int(col.r_v[i]) - 1, n_x + i) for i in range(n_x)]
+                     + [(("t0",), p.info_t_0, col.L - 2, 2 * n_x), (("tf",), p.info_t_f, col.L - 1, 2 * n_x + 1)])
+            bnd = [("bV_" + "_".join(str(v) for v in tag), info.v.expr) for tag, info, _, _ in infos if info.t == BcType.FUNC]
+            if bnd:
+                L.append(emit_block(bnd, names, prefix="cb").rstrip("\n"))
+            add("    double v = xp[k];")
+            for tag, info, slot, fix_index in infos:
+                if info.t == BcType.FIXED:
+                    add(f"    if (k == {slot}) v = fix[{fix_index}];")
+                elif info.t == BcType.FUNC:
+                    add(f"    if (k == {slot}) v = bV_{'_'.join(str(q) for q in tag)};")
+            add(f"    XS[(long long)b * {col.L} + k] = v;")
+            add("}")
+            # --- node: dynamics at the augmented nodes
+            add(f'extern "C" __global__ void {node}(const double* __restrict__ X, const double* __restrict__ XS,')
+            add("    const double* __restrict__ XU, const double* __restrict__ TMA, double* __restrict__ WA, int B)")
+            add("{")
+            add("    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;")
+            add(f"    if (gid >= (long long)B * {A.L_m}) return;")
+            add(f"    const int b = (int)(gid / {A.L_m});")
+            add(f"    const int c = (int)(gid - (long long)b * {A.L_m});")
+            add(f"    const double* sv = X + (long long)b * {lo.r_s} + {lo.l_s};")
+            names = {}
+            for k, sym in enumerate(p.s):
+                add(f"    const double s{k} = sv[{k}];")
+                names[sym] = f"s{k}"
+            add(f"    const double* xsb = XS + (long long)b * {col.L};")
+            add(f"    const double t0 = xsb[{col.L - 2}], tf = xsb[{col.L - 1}];")
+            add("    const double dt = tf - t0;")
+            add("    const double mt = (tf + t0) / 2.0;")
+            add("    const double t = (TMA[c] - 0.5) * dt + mt;")
+            names[p.t] = "t"
+            add(f"    const double* xu = XU + (long long)b * {(n_x + n_u) * A.L_m};")
+            for i, sym in enumerate(p.x):
+                add(f"    const double x{i} = xu[{i * A.L_m}LL + c];")
+                names[sym] = f"x{i}"
+            for j, sym in enumerate(p.u):
+                add(f"    const double u{j} = xu[{(n_x + j) * A.L_m}LL + c];")
+                names[sym] = f"u{j}"
+            leaves = [(f"F_d_{i}", p.F_d[i].expr) for i in range(n_x)]
+            if leaves:
+                L.append(emit_block(leaves, names, prefix="ce").rstrip("\n"))
+            for i in range(n_x):
+                add(f"    WA[((long long)b * {n_x} + {i}) * {A.L_m} + c] = F_d_{i};")
+            add("}")
+            body.append("\n".join(L))
+            phases.append(dict(prep=prep, node=node, x_offset=int(lo.l_p[pi]), L=int(col.L), L_xu=int(col.L_xu),
+                               L_x_all=int(col.r_v[n_x - 1]) if n_x else 0, n_x=n_x, n_u=n_u, Lm_aug=int(A.L_m),
+                               rows=int(A.rows), tm_aug=np.ascontiguousarray(A.t_m), V=A.V, T=A.T, I=A.I, aug=A))
+        head = ["// generated by pockit_b200.plan -- continuous error-estimate programs", PRELUDE]
+        return dict(source="\n".join(head + body) + "\n", phases=phases)
+
     def _sys_kernel(self, mp: ModePlan, kname: str) -> str:
         lo = self.lo
         name = MODES[mp.mode]

@@ -272,6 +272,37 @@ class System:
         names = {P.OBJ: "objective", P.GRAD: "gradient", P.CONS: "constraints", P.JAC: "jacobian", P.HESS: "hessian"}
         return {names[m]: v for m, v in res.items()}
 
+    # ------------------------------------------------------------------ mesh-refinement data (device)
+    def error_estimation_data(self, x):
+        """Per phase ``(T_x_aug, I_f_aug)`` at the optimisation vector ``x`` -- what
+        ``PhaseBase._error_estimation_data_continuous(x_phase, s)`` (``phasebase.py:1355-1366``)
+        returns for every phase: the state interpolant's increments and the integrated dynamics on
+        the augmented mesh (one more point per interval)."""
+        return self.engine.error_estimation_data(x)
+
+    def check_continuous(self, x, absolute_tolerance_continuous: float = 1e-8, relative_tolerance_continuous: float = 1e-8,
+                         tolerance_mesh: float = 1e-4):
+        """Per phase, which intervals pass the continuous error check
+        (``_error_check_interval_continuous``, ``phasebase.py:1375-1386``; intervals narrower than
+        ``tolerance_mesh`` always pass).  ``all(map(np.all, result))`` is the reference's
+        ``check_continuous`` verdict for the whole system."""
+        from .discretization import AugmentedCollocation
+
+        out = []
+        for p, (T, I) in zip(self._phase, self.error_estimation_data(x)):
+            if not hasattr(p, "_aug_cache") or p._aug_cache[0] != p._version:
+                p._aug_cache = (p._version, AugmentedCollocation(p.col))
+            A = p._aug_cache[1]
+            # rows of interval k: the augmented-mesh nodes of the interval, like the reference's l_m_aug / r_m_aug
+            ok = np.ones(len(p.col.num_point), dtype=bool)
+            for k in range(len(ok)):
+                if p.col.mesh[k + 1] - p.col.mesh[k] < tolerance_mesh:
+                    continue
+                l, r = int(A.l_m[k]), int(A.r_m[k])
+                ok[k] = np.allclose(T[:, l:r], I[:, l:r], atol=absolute_tolerance_continuous, rtol=relative_tolerance_continuous)
+            out.append(ok)
+        return out
+
     def objective(self, x):
         return self.engine.objective(x)
 

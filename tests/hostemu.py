@@ -230,3 +230,47 @@ class HostEmu:
                 v = v * LAM[b, i[2] + K * rows + r]
             for dst, wbase in lists:
                 OUT[b, dst : dst + len(e)] = v * W[wbase + b * i[10] + c0 + K * step + cc]
+
+
+def emulate_error_data(system, x):
+    """Host emulation of the engine's continuous error-estimate path (``pk_eval_error_data``): the
+    generated prep / node programs compiled as C++ and run thread by thread, the three CSR operators
+    applied with SciPy (sequential row sums, like the device kernel).  B = 1."""
+    lo = system.lowering
+    dp = P.DevicePlan(lo)
+    ee = dp.error_estimate()
+    drivers = []
+    for ph in ee["phases"]:
+        drivers.append(
+            f'extern "C" void run_{ph["prep"]}(const double* X, const double* FIX, double* XS, long long threads) {{\n'
+            f"  blockDim.x = 128;\n  for (long long g = 0; g < threads; ++g) {{ blockIdx.x = g / 128; threadIdx.x = g % 128;\n"
+            f'    {ph["prep"]}(X, FIX, XS, 1); }}\n}}\n'
+            f'extern "C" void run_{ph["node"]}(const double* X, const double* XS, const double* XU, const double* TMA, double* WA,'
+            f" long long threads) {{\n  blockDim.x = 128;\n"
+            f"  for (long long g = 0; g < threads; ++g) {{ blockIdx.x = g / 128; threadIdx.x = g % 128;\n"
+            f'    {ph["node"]}(X, XS, XU, TMA, WA, 1); }}\n}}\n'
+        )
+    text = SHIM + ee["source"] + "\n".join(drivers)
+    _CACHE.mkdir(exist_ok=True)
+    key = hashlib.sha256(text.encode()).hexdigest()[:24]
+    so = _CACHE / f"{key}.so"
+    if not so.exists():
+        cpp = _CACHE / f"{key}.cpp"
+        cpp.write_text(text)
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(cpp)])
+    lib = ctypes.CDLL(str(so))
+    X = np.ascontiguousarray(np.asarray(x, float))
+    FIX = np.ascontiguousarray(dp.fixed_default) if dp.n_fixed else np.zeros(1)
+    out = []
+    for ph in ee["phases"]:
+        XS = np.full(ph["L"], np.nan)
+        getattr(lib, "run_" + ph["prep"])(_ptr(X), _ptr(FIX), _ptr(XS), ctypes.c_longlong(ph["L"]))
+        XU = np.ascontiguousarray(ph["V"].dot(XS[: ph["L_xu"]]))
+        WA = np.full(max(1, ph["n_x"] * ph["Lm_aug"]), np.nan)
+        tm = np.ascontiguousarray(ph["tm_aug"])
+        getattr(lib, "run_" + ph["node"])(_ptr(X), _ptr(XS), _ptr(XU), _ptr(tm), _ptr(WA), ctypes.c_longlong(ph["Lm_aug"]))
+        TX = ph["T"].dot(XS[: ph["L_x_all"]]).reshape(ph["n_x"], -1)
+        dt = XS[-1] - XS[-2]
+        IF = np.array([ph["I"].dot(WA[i * ph["Lm_aug"] : (i + 1) * ph["Lm_aug"]]) * dt for i in range(ph["n_x"])]).reshape(ph["n_x"], -1)
+        out.append((TX, IF))
+    return out
