@@ -56,6 +56,9 @@ struct ModeState {
   cudaEvent_t done = nullptr;
   cudaStream_t side = nullptr;        // the small slot runs overlap the block expansion
   cudaEvent_t side_fork = nullptr, side_join = nullptr;
+  // two more branches of the small-kernel DAG (defects / gradient gather run beside the reduction chain)
+  cudaStream_t aux1 = nullptr, aux2 = nullptr;
+  cudaEvent_t sys_done = nullptr, aux1_join = nullptr, aux2_join = nullptr;
   std::vector<char> cubin;
   pk_job* jobs[PK_N_STAGES] = {};
   long long n_jobs[PK_N_STAGES] = {};
@@ -209,6 +212,11 @@ static void free_mode(ModeState& ms) {
   if (ms.side) cudaStreamDestroy(ms.side);
   if (ms.side_fork) cudaEventDestroy(ms.side_fork);
   if (ms.side_join) cudaEventDestroy(ms.side_join);
+  if (ms.aux1) cudaStreamDestroy(ms.aux1);
+  if (ms.aux2) cudaStreamDestroy(ms.aux2);
+  if (ms.sys_done) cudaEventDestroy(ms.sys_done);
+  if (ms.aux1_join) cudaEventDestroy(ms.aux1_join);
+  if (ms.aux2_join) cudaEventDestroy(ms.aux2_join);
   if (ms.red_partial) cudaFree(ms.red_partial);
   if (ms.red_ticket) cudaFree(ms.red_ticket);
   if (ms.cp_ptr) cudaFree(ms.cp_ptr);
@@ -473,6 +481,11 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     CK(cudaStreamCreateWithPriority(&ms.side, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaEventCreateWithFlags(&ms.side_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ms.side_join, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithPriority(&ms.aux1, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
+    CK(cudaStreamCreateWithPriority(&ms.aux2, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
+    CK(cudaEventCreateWithFlags(&ms.sys_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ms.aux1_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ms.aux2_join, cudaEventDisableTiming));
   }
   if (e->set_graph) {  // a re-loaded mode invalidates the captured set
     cudaGraphExecDestroy(e->set_graph);
@@ -600,19 +613,32 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
     }
     tr(e, mode, 6, 1, st);
   }
-  // The block expansion only reads the node table, so it starts right behind the per-node programs
-  // on `st`; everything latency-bound -- reductions, system program, defects, the small slot runs,
-  // the gradient gather -- runs as one chain on the side stream and hides behind it.
+  // Dependencies after the per-node programs (N):
+  //   block expansion          <- N                      (only reads the node table)       stream st
+  //   reductions -> system program (SYS) -> small slot runs   <- N                         stream ss
+  //   defects                  <- N                                                        stream a1
+  //   gradient: zero fill <- nothing; range gather <- SYS, zero fill                       stream a2
+  //             scalar gather <- SYS                                                        stream a1
+  // With an expansion, ss is the side stream and everything latency-bound hides behind it; a
+  // whole-mode launch spreads the three small branches over ss / a1 / a2, a stage-masked one
+  // (pk_time) keeps them on st in this order.
+  const bool whole = stage_mask == ~0u;
   const bool run_exp = on(PK_STAGE_EXPAND) && !ms.exp.empty();
-  const bool small = (on(PK_STAGE_REDUCE) && ms.n_jobs[PK_STAGE_REDUCE]) || (on(PK_N_STAGES + 1) && ms.sys_kernel) ||
-                     (on(PK_STAGE_DEFECT) && ms.n_jobs[PK_STAGE_DEFECT]) || (on(PK_STAGE_GENERIC) && ms.gen_blocks) ||
-                     (ms.grad_cnt && (on(PK_STAGE_GRAD_RANGE) || on(PK_STAGE_GRAD_SCALAR)));
+  const bool run_red = on(PK_STAGE_REDUCE) && ms.n_jobs[PK_STAGE_REDUCE];
+  const bool run_sys = on(PK_N_STAGES + 1) && ms.sys_kernel;
+  const bool run_def = on(PK_STAGE_DEFECT) && ms.n_jobs[PK_STAGE_DEFECT];
+  const bool run_gen = on(PK_STAGE_GENERIC) && ms.gen_blocks;
+  const bool run_grad = ms.grad_cnt && (on(PK_STAGE_GRAD_RANGE) || on(PK_STAGE_GRAD_SCALAR));
+  const bool small = run_red || run_sys || run_def || run_gen || run_grad;
   const bool fork = run_exp && small;
-  cudaStream_t ss = fork ? ms.side : st;  // stream of the small chain
-  if (fork) {
-    CK(cudaEventRecord(ms.side_fork, st));
-    CK(cudaStreamWaitEvent(ms.side, ms.side_fork, 0));
-  }
+  cudaStream_t ss = fork ? ms.side : st;
+  const bool use_a1 = whole && (run_def || (run_grad && ms.n_jobs[PK_STAGE_GRAD_SCALAR])) && (run_red || run_sys || run_gen || fork);
+  const bool use_a2 = whole && run_grad && (run_red || run_sys);
+  cudaStream_t a1 = use_a1 ? ms.aux1 : ss, a2 = use_a2 ? ms.aux2 : ss;
+  if (fork || use_a1 || use_a2) CK(cudaEventRecord(ms.side_fork, st));
+  if (fork) CK(cudaStreamWaitEvent(ms.side, ms.side_fork, 0));
+  if (use_a1) CK(cudaStreamWaitEvent(ms.aux1, ms.side_fork, 0));
+  if (use_a2) CK(cudaStreamWaitEvent(ms.aux2, ms.side_fork, 0));
   if (run_exp) {
     tr(e, mode, PK_STAGE_EXPAND, 0, st);
     if (e->chain && e->chain_last >= 0) CK(cudaStreamWaitEvent(st, e->chain_ev[e->chain_last], 0));
@@ -621,7 +647,26 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
     e->launches += (long long)ms.exp.size();
     tr(e, mode, PK_STAGE_EXPAND, 1, st);
   }
-  if (on(PK_STAGE_REDUCE) && ms.n_jobs[PK_STAGE_REDUCE]) {
+  if (run_grad) {  // zero fill first: it depends on nothing
+    CK(cudaMemset2DAsync(ms.OUT + ms.grad_off, sizeof(double) * (size_t)ms.n_out, 0, sizeof(double) * (size_t)ms.grad_cnt, (size_t)B, a2));
+    if (a1 != a2 && ms.n_jobs[PK_STAGE_GRAD_SCALAR]) CK(cudaEventRecord(ms.aux2_join, a2));  // the scalar gather writes filled slots
+  }
+  if (run_def) {
+    dim3 grid(blocks_for(ms.max_defect_rows * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_DEFECT]);
+    if (ms.def_table) {
+      pk_defects<<<grid, PK_THREADS, 0, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+      ++e->launches;
+    }
+    if (ms.def_fast) {
+      if (ms.idx32)
+        pk_defects_blocks<unsigned><<<grid, PK_THREADS, ms.def_smem, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+      else
+        pk_defects_blocks<unsigned long long><<<grid, PK_THREADS, ms.def_smem, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+      ++e->launches;
+    }
+    tr(e, mode, PK_STAGE_DEFECT, 1, a1);
+  }
+  if (run_red) {
     const long long warps = ms.n_jobs[PK_STAGE_REDUCE] * (long long)B;
     if (ms.red_parts)
       pk_reduce_rows_block<<<(unsigned)(warps * ms.red_parts), PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_REDUCE], (int)ms.n_jobs[PK_STAGE_REDUCE], B,
@@ -631,29 +676,19 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
     ++e->launches;
     tr(e, mode, PK_STAGE_REDUCE, 1, ss);
   }
-  if (on(PK_N_STAGES + 1) && ms.sys_kernel) {
+  if (run_sys) {
     int Bi = B;
     void* args[] = {&e->X, &ms.S, &ms.OUT, &Bi};
     CK(cudaLaunchKernel((void*)ms.sys_kernel, dim3(blocks_for(B, 64)), dim3(64), args, 0, ss));
     ++e->launches;
     tr(e, mode, 7, 1, ss);
   }
-  if (on(PK_STAGE_DEFECT) && ms.n_jobs[PK_STAGE_DEFECT]) {
-    dim3 grid(blocks_for(ms.max_defect_rows * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_DEFECT]);
-    if (ms.def_table) {
-      pk_defects<<<grid, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
-      ++e->launches;
-    }
-    if (ms.def_fast) {
-      if (ms.idx32)
-        pk_defects_blocks<unsigned><<<grid, PK_THREADS, ms.def_smem, ss>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
-      else
-        pk_defects_blocks<unsigned long long><<<grid, PK_THREADS, ms.def_smem, ss>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
-      ++e->launches;
-    }
-    tr(e, mode, PK_STAGE_DEFECT, 1, ss);
+  if ((use_a1 || use_a2) && (run_red || run_sys)) {
+    CK(cudaEventRecord(ms.sys_done, ss));
+    if (use_a1) CK(cudaStreamWaitEvent(ms.aux1, ms.sys_done, 0));
+    if (use_a2) CK(cudaStreamWaitEvent(ms.aux2, ms.sys_done, 0));
   }
-  if (on(PK_STAGE_GENERIC) && ms.gen_blocks) {
+  if (run_gen) {
     if (ms.idx32)
       pk_generic_jobs<unsigned><<<(unsigned)ms.gen_blocks, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GENERIC], ms.gen_job, ms.gen_chunk, B);
     else
@@ -661,22 +696,30 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
     ++e->launches;
     tr(e, mode, PK_STAGE_GENERIC, 1, ss);
   }
-  if (ms.grad_cnt && (on(PK_STAGE_GRAD_RANGE) || on(PK_STAGE_GRAD_SCALAR))) {
-    CK(cudaMemset2DAsync(ms.OUT + ms.grad_off, sizeof(double) * (size_t)ms.n_out, 0, sizeof(double) * (size_t)ms.grad_cnt, (size_t)B, ss));
+  if (run_grad) {
     if (ms.n_jobs[PK_STAGE_GRAD_RANGE]) {
       dim3 grid(blocks_for(ms.max_grad_count * B, PK_THREADS), (unsigned)ms.n_jobs[PK_STAGE_GRAD_RANGE]);
       if (ms.idx32)
-        pk_grad_range<unsigned><<<grid, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
+        pk_grad_range<unsigned><<<grid, PK_THREADS, 0, a2>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
       else
-        pk_grad_range<unsigned long long><<<grid, PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
+        pk_grad_range<unsigned long long><<<grid, PK_THREADS, 0, a2>>>(cx, ms.jobs[PK_STAGE_GRAD_RANGE], B);
       ++e->launches;
     }
     if (ms.n_jobs[PK_STAGE_GRAD_SCALAR]) {
+      if (a1 != a2) CK(cudaStreamWaitEvent(a1, ms.aux2_join, 0));  // behind the zero fill
       const long long n = ms.n_jobs[PK_STAGE_GRAD_SCALAR] * (long long)B;
-      pk_grad_scalar<<<blocks_for(n, PK_THREADS), PK_THREADS, 0, ss>>>(cx, ms.jobs[PK_STAGE_GRAD_SCALAR], (int)ms.n_jobs[PK_STAGE_GRAD_SCALAR], B);
+      pk_grad_scalar<<<blocks_for(n, PK_THREADS), PK_THREADS, 0, a1>>>(cx, ms.jobs[PK_STAGE_GRAD_SCALAR], (int)ms.n_jobs[PK_STAGE_GRAD_SCALAR], B);
       ++e->launches;
     }
-    tr(e, mode, PK_STAGE_GRAD_RANGE, 1, ss);
+    tr(e, mode, PK_STAGE_GRAD_RANGE, 1, a2);
+  }
+  if (use_a1) {
+    CK(cudaEventRecord(ms.aux1_join, ms.aux1));
+    CK(cudaStreamWaitEvent(st, ms.aux1_join, 0));
+  }
+  if (use_a2) {
+    CK(cudaEventRecord(ms.aux2_join, ms.aux2));
+    CK(cudaStreamWaitEvent(st, ms.aux2_join, 0));
   }
   if (fork) {
     CK(cudaEventRecord(ms.side_join, ms.side));
