@@ -83,7 +83,8 @@ class _SharedBuffers:
 
 class MeshShardedSystem:
     def __init__(self, system, rank: Optional[int] = None, world: Optional[int] = None, device: Optional[int] = None,
-                 make_engine: Optional[Callable] = None, page_lock: bool = True, shm_dir: str = "/dev/shm"):
+                 make_engine: Optional[Callable] = None, page_lock: bool = True, shm_dir: str = "/dev/shm",
+                 _startup_delay: float = 0.0):
         self.system = system
         self.rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
         self.world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else int(world)
@@ -119,7 +120,12 @@ class MeshShardedSystem:
         if page_lock and hasattr(self.engine, "lib"):
             self.engine._check(self.engine.lib.pk_host_register(self.buf.address, self.buf.size))
             self._locked = True
-        self._seq = int(self.buf.ctrl[0])
+        if _startup_delay:  # test hook: a rank that finishes its start-up late (slow page-locking)
+            time.sleep(_startup_delay)
+        # the mapping starts zeroed; do NOT read the live counter here: rank 0 may already have published
+        # its first point while this rank was still page-locking the mapping (seen at 8 ranks: a worker
+        # that read 1 waited for the counter to change forever)
+        self._seq = 0
         self.pinned_outputs = False
         self._closed = False
 
@@ -132,7 +138,7 @@ class MeshShardedSystem:
 
     # ------------------------------------------------------------------ worker side
     @staticmethod
-    def _wait(cond, what: str, timeout: float = 600.0):
+    def _wait(cond, what: str, timeout: float = 120.0):
         t0 = time.perf_counter()
         spins = 0
         while not cond():

@@ -125,7 +125,9 @@ def _mesh_worker(rank, world, port, q):
         def objective(self, x):
             return self.e.run(P.OBJ, x)[0]
 
-    ms = MeshShardedSystem(S, make_engine=EmuEngine)
+    # rank 1 finishes its start-up late: rank 0 has published its first point by then (regression:
+    # a worker that initialised its sequence number from the live counter waited forever)
+    ms = MeshShardedSystem(S, make_engine=EmuEngine, _startup_delay=1.5 if rank == 1 else 0.0)
     if rank != 0:
         ms.serve()
     else:
