@@ -143,8 +143,9 @@ class MeshShardedSystem:
         spins = 0
         while not cond():
             spins += 1
-            if spins > 20000:  # ~ a few ms of polling, then yield the core
-                time.sleep(0.0002)
+            if spins > 2000:  # a short burst of polling (a set takes ~1 ms), then stop hogging the core:
+                # with one process per GPU the pollers otherwise compete with rank 0 for host cores
+                time.sleep(0.00002 if spins < 20000 else 0.0005)
                 if time.perf_counter() - t0 > timeout:
                     raise TimeoutError(f"mesh shard: timed out waiting for {what}")
 
