@@ -37,6 +37,11 @@ class Variable:
         col = phase.col
         self._t_x = col.t_m if col.scheme == "lgl" else np.concatenate([col.t_m, [1.0]])
 
+        self._t_u = col.t_m
+
+    # physical times of the state / control nodes (``variablebase.py:355-363``)
+    t_x = property(lambda self: self._t_x * (self.t_f - self.t_0) + self.t_0)
+    t_u = property(lambda self: self._t_u * (self.t_f - self.t_0) + self.t_0)
     t_0 = property(lambda self: self.data[-2], lambda self, v: self.data.__setitem__(-2, v))
     t_f = property(lambda self: self.data[-1], lambda self, v: self.data.__setitem__(-1, v))
 

@@ -280,6 +280,39 @@ def tiny(mod, mesh=1, num_point=3):
     return S
 
 
+def check_system(mod):
+    """The reference's known-answer system for the continuous error check
+    (``tests/test_labatto/test_check_lobatto.py:7-36``, same for radau): ``x' = u`` on a two-interval
+    mesh, with trajectories that are exact polynomials (must pass) and perturbed ones (must fail).
+    Returns ``(system, [(value, expected), ...])`` with ``value = [Variable, statics]``."""
+    from .guess import constant_guess
+
+    S = mod.System(1)
+    p = S.new_phase(1, 1)
+    p.set_dynamics([p.u[0]])
+    p.set_boundary_condition([None], [None], None, None)
+    p.set_phase_constraint([p.u[0] + S.s[0]], [0.0], [2.0], [True])
+    p.set_discretization([0, 0.1, 1], [3, 4])
+    S.set_phase([p])
+    S.set_objective(S.s[0])
+
+    def variable(x_of_t, u_of_t, bump=0.0):
+        v = constant_guess(p, 1.0)
+        v.x[0] = x_of_t(v.t_x)
+        v.u[0] = u_of_t(v.t_u)
+        v.u[0][0] += bump
+        return [v, [0.0]]
+
+    one = lambda t: np.ones_like(t)  # noqa: E731
+    cases = [
+        (variable(lambda t: t, one), True),
+        (variable(lambda t: t**2, lambda t: 2 * t), True),
+        (variable(lambda t: t**2, lambda t: 2 * t, bump=0.01), False),
+        (variable(lambda t: t**2, lambda t: 1.99 * t), False),
+    ]
+    return S, cases
+
+
 BUILDERS = {
     "static_only": static_only, "no_control": no_control, "tiny": tiny,
     "lqr": lqr, "robot_arm": robot_arm, "humanoid": humanoid, "rocket": rocket,

@@ -23,7 +23,7 @@ from .chain import ONE, GEntry, HEntry, Sym, Term, compose, leaf
 from .phase import BcType, Phase, PhaseLowering, Segment
 from .symfunc import SymFunc
 
-__all__ = ["System", "SysSegment", "SystemLowering"]
+__all__ = ["System", "SysSegment", "SystemLowering", "continuous_error_intervals"]
 
 
 @dataclass
@@ -280,28 +280,36 @@ class System:
         the augmented mesh (one more point per interval)."""
         return self.engine.error_estimation_data(x)
 
-    def check_continuous(self, x, absolute_tolerance_continuous: float = 1e-8, relative_tolerance_continuous: float = 1e-8,
-                         tolerance_mesh: float = 1e-4):
-        """Per phase, which intervals pass the continuous error check
-        (``_error_check_interval_continuous``, ``phasebase.py:1375-1386``; intervals narrower than
-        ``tolerance_mesh`` always pass).  ``all(map(np.all, result))`` is the reference's
-        ``check_continuous`` verdict for the whole system."""
-        from .discretization import AugmentedCollocation
+    def check_continuous_intervals(self, x, absolute_tolerance_continuous: float = 1e-8,
+                                   relative_tolerance_continuous: float = 1e-8, tolerance_mesh: float = 1e-4):
+        """Per phase, which intervals pass the continuous error check at the optimisation vector ``x``."""
+        data = self.error_estimation_data(x)
+        return [continuous_error_intervals(p, T, I, absolute_tolerance_continuous, relative_tolerance_continuous, tolerance_mesh)
+                for p, (T, I) in zip(self._phase, data)]
 
-        out = []
-        for p, (T, I) in zip(self._phase, self.error_estimation_data(x)):
-            if not hasattr(p, "_aug_cache") or p._aug_cache[0] != p._version:
-                p._aug_cache = (p._version, AugmentedCollocation(p.col))
-            A = p._aug_cache[1]
-            # rows of interval k: the augmented-mesh nodes of the interval, like the reference's l_m_aug / r_m_aug
-            ok = np.ones(len(p.col.num_point), dtype=bool)
-            for k in range(len(ok)):
-                if p.col.mesh[k + 1] - p.col.mesh[k] < tolerance_mesh:
-                    continue
-                l, r = int(A.l_m[k]), int(A.r_m[k])
-                ok[k] = np.allclose(T[:, l:r], I[:, l:r], atol=absolute_tolerance_continuous, rtol=relative_tolerance_continuous)
-            out.append(ok)
-        return out
+    def check_continuous(self, value, absolute_tolerance_continuous: float = 1e-8, relative_tolerance_continuous: float = 1e-8,
+                         tolerance_mesh: float = 1e-4) -> bool:
+        """``True`` if the continuous error of ``value`` is within the tolerance on every interval of
+        every phase (``SystemBase.check_continuous``, ``systembase.py:837-900``).  ``value`` is what the
+        reference takes -- a ``Variable``, or a list of them followed by the static parameters -- or
+        the flat optimisation vector."""
+        if isinstance(value, np.ndarray):
+            if not self.ok:
+                raise ValueError("system is not fully configured")
+            x = value
+        else:
+            from .optimizer._common import pack_guess
+
+            try:
+                x, _, _ = pack_guess(self, value, None)
+            except ValueError as exc:  # the reference's wording for this entry point
+                raise ValueError(str(exc).replace("len(guess)", "len(value)")) from None
+        return all(bool(np.all(ok)) for ok in self.check_continuous_intervals(
+            x, absolute_tolerance_continuous, relative_tolerance_continuous, tolerance_mesh))
+
+    def check_discontinuous(self, value, *args, **kwargs):
+        """Bang-bang (discontinuous) error check: not part of this engine (``phasebase.py:1439-1474``)."""
+        raise NotImplementedError("the discontinuous error check is outside the scope of the B200 engine")
 
     def objective(self, x):
         return self.engine.objective(x)
@@ -323,6 +331,25 @@ class System:
 
     def hessian(self, x, fct_c, fct_o):
         return self.engine.hessian(x, fct_c, fct_o)
+
+
+def continuous_error_intervals(phase, T_x_aug, I_f_aug, atol: float, rtol: float, mtol: float) -> np.ndarray:
+    """Per interval, whether the state increments of the interpolant match the integrated dynamics on
+    the augmented mesh (``_error_check_interval_continuous``, ``phasebase.py:1375-1386``).  Intervals
+    narrower than ``mtol`` always pass; the column ranges are the reference's ``l_m_aug`` / ``r_m_aug``."""
+    from .discretization import AugmentedCollocation
+
+    if getattr(phase, "_aug_cache", (None,))[0] != phase._version:
+        phase._aug_cache = (phase._version, AugmentedCollocation(phase.col))
+    A = phase._aug_cache[1]
+    col = phase.col
+    ok = np.ones(len(col.num_point), dtype=bool)
+    for k in range(len(ok)):
+        if col.mesh[k + 1] - col.mesh[k] < mtol:
+            continue
+        l, r = int(A.l_m[k]), int(A.r_m[k])
+        ok[k] = np.allclose(T_x_aug[:, l:r], I_f_aug[:, l:r], atol=atol, rtol=rtol)
+    return ok
 
 
 def _translate(idx: np.ndarray, l_p: int, r_s: int) -> np.ndarray:

@@ -62,3 +62,24 @@ def test_generated_error_programs_match_reference(case):
     for i, (T, I) in enumerate(got):
         assert_close(T, g[f"T_{i}"], f"T_x_aug[{i}]")
         assert_close(I, g[f"I_{i}"], f"I_f_aug[{i}]")
+
+
+@pytest.mark.parametrize("scheme", ["lobatto", "radau"])
+def test_check_continuous_known_answers_on_the_host_emulated_programs(scheme):
+    """The reference's known-answer test of the continuous check
+    (tests/test_labatto/test_check_lobatto.py:22-36): exact polynomial trajectories pass, perturbed
+    ones fail -- here with the generated programs emulated on the host feeding the interval test."""
+    import importlib
+
+    sys.path.insert(0, str(GOLDEN.parent))
+    from hostemu import emulate_error_data
+    from pockit_b200 import problems
+    from pockit_b200.optimizer._common import pack_guess
+    from pockit_b200.system import continuous_error_intervals
+
+    S, cases = problems.check_system(importlib.import_module(f"pockit_b200.{scheme}"))
+    for value, expected in cases:
+        x, _, _ = pack_guess(S, value, None)
+        (T, I), = emulate_error_data(S, x)
+        ok = continuous_error_intervals(S.p[0], T, I, 1e-8, 1e-8, 1e-4)
+        assert bool(ok.all()) is expected
