@@ -21,8 +21,8 @@ def test_generated_cuda_compiles_for_sm100a(case):
     for m in range(6):
         dp.mode(m)
     with tempfile.TemporaryDirectory() as tmp:
-        for m in range(6):
-            src = dp.finalize(m)["source"]
+        for m in range(7):  # the five callbacks, the fused set pipeline, the error-estimate programs
+            src = dp.finalize(m)["source"] if m < 6 else dp.error_estimate()["source"]
             cu = Path(tmp) / f"mode{m}.cu"
             cu.write_text(src)
             r = subprocess.run(

@@ -162,3 +162,14 @@ def test_tools_parse():
     root = Path(__file__).resolve().parent.parent
     for f in sorted((root / "tools").glob("*.py")) + [root / "bench.py", root / "__graft_entry__.py"]:
         py_compile.compile(str(f), doraise=True)
+
+
+def test_mirrored_hessian_known_answer():
+    """The reference's own test of the lower-triangle -> full matrix reflection
+    (tests/test_optimizer/test_optimizer_scipy.py:7-15): duplicates summed, diagonal counted once."""
+    from pockit_b200.optimizer.scipy import _mirrored
+
+    row = np.array([3, 2, 2, 0, 2, 2, 1])
+    col = np.array([3, 2, 0, 0, 1, 2, 0])
+    full = _mirrored(lambda _: np.arange(7) ** 2, row, col, 4)(None).toarray()
+    assert np.all(full == np.array([[9, 36, 4, 0], [36, 0, 16, 0], [4, 16, 1 + 25, 0], [0, 0, 0, 0]]))
