@@ -353,9 +353,12 @@ def main():
     traffic = None
     tr = ROOT / "profiles" / "r01_expand_traffic_v8.json"
     if tr.exists():  # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture
-        recs = [r for r in json.loads(tr.read_text())["launches"] if r["kernel"].split(" ")[0] == kernel.split(" ")[0]]
-        if recs:
-            traffic = recs[-1]["dram_read_bytes"] + recs[-1]["dram_write_bytes"]
+        name = kernel.split(" ")[0]
+        recs = [r for r in json.loads(tr.read_text())["launches"] if r["kernel"].startswith(name)]
+        hess = [r for r in recs if "<1>" in r["kernel"]]  # template argument LAM = true: the Hessian launch
+        if hess or recs:
+            rec = (hess or recs)[-1]
+            traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
     set_bytes = 8 * (6 * L + 2 * m + nj + nh)
     per_mode = {}
     for mname, mm in zip(("objective", "gradient", "constraints", "jacobian", "hessian"), modes):
