@@ -158,7 +158,8 @@ class Engine:
         self.B = int(batch)
         self.shard = shard
         self.plan = P.DevicePlan(lowering, self.B, fastmath, shard=shard,
-                                 fused=shard is None and os.environ.get("POCKIT_B200_FUSED", "0") == "1")
+                                 fused=shard is None and os.environ.get("POCKIT_B200_FUSED", "0") == "1",
+                                 node_groups=int(os.environ.get("POCKIT_B200_NODE_GROUPS", "1")))
         self.fin = {}
         # The fused set pipeline (plan.SET: one per-node program, one reduction, one system program for
         # all five callbacks) is opt-in, POCKIT_B200_SET=1: measured on B200 (round 1, tools/probe3.py) it
@@ -230,7 +231,8 @@ class Engine:
         lo = self.lowering
         progs = (_NodeProgram * max(1, len(f["kernels"])))()
         for pi, k in enumerate(f["kernels"]):
-            progs[pi] = _NodeProgram(k.encode(), lo.phases[pi].L_m, self.plan.tm_off[pi], self.plan.wm_off[pi])
+            # threads per instance: nodes x expression groups of the phase's program
+            progs[pi] = _NodeProgram(k.encode(), lo.phases[pi].L_m * f["node_threads"][pi], self.plan.tm_off[pi], self.plan.wm_off[pi])
         opts = (C.c_char_p * max(1, len(self._opts)))(*[o.encode() for o in self._opts])
         table = np.ascontiguousarray(f["table"], dtype=np.int64)
         d = _ModeDesc()

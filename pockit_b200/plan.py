@@ -20,6 +20,7 @@ Data layout in HBM (per engine, ``B`` instances)::
 """
 from __future__ import annotations
 
+import re
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -86,6 +87,17 @@ class Pools:
         return np.ascontiguousarray(d), np.ascontiguousarray(i)
 
 
+_FN_LEAF = re.compile(r"\b[FGH]_([dIc])_(\d+)(?:_\d+)?\b")
+
+
+def _function_of(code) -> Optional[tuple]:
+    """(family, index) of the function whose leaves a store term uses (each term uses one), or None."""
+    if not isinstance(code, str):
+        return None
+    m = _FN_LEAF.search(code)
+    return (m.group(1), int(m.group(2))) if m else None
+
+
 def _ident(leaf: Leaf) -> str:
     return leaf.kind + "_" + "_".join(str(k) for k in leaf.key) if leaf.key else leaf.kind
 
@@ -134,6 +146,7 @@ class ModePlan:
         self.src = None
         self.expand_groups: dict = {}
         self.owned_runs: Optional[list] = None  # mesh shard: (offset, count) runs of the output computed here
+        self.node_threads = [1] * len(lo.phases)  # threads per node of every phase's program (expression groups)
         self.sub = mode   # callback currently being planned (differs from `mode` only inside SET)
         self.base = 0     # first output slot of that callback
         self.sub_range: dict = {}  # SET: callback -> (offset, count) inside the combined output
@@ -570,7 +583,7 @@ class DevicePlan:
     """Pools + per-mode plans for one lowered system."""
 
     def __init__(self, lo: SystemLowering, batch: int = 1, fastmath: bool = False, fused: bool = False,
-                 shard: Optional[tuple] = None):
+                 shard: Optional[tuple] = None, node_groups: int = 1):
         self.lo = lo
         self.B = int(batch)
         self.fastmath = fastmath
@@ -582,6 +595,10 @@ class DevicePlan:
                 raise ValueError("mesh sharding is not available with the fused expansion variant")
             shard = (g, G)
         self.shard = shard
+        # node_groups > 1: up to that many threads per node, one per group of functions (measured
+        # default pending: it shortens the latency-bound per-node programs at the price of
+        # re-evaluating subexpressions the functions share)
+        self.node_groups = max(1, int(node_groups))
         # fused=True: the per-node program itself walks its block column and writes the slots (no
         # node-table round trip, one launch less).  Measured on B200 (round 1) it is SLOWER than the
         # node program + persistent pk_expand_blocks pair (robot_arm Hessian 40 us vs 31 us, humanoid
@@ -785,8 +802,30 @@ class DevicePlan:
             source=src, kernels=kernels, sys_kernel=sys_name, table=np.array(mp.table, dtype=np.int64),
             table_symbol=f"pk_tab_{MODES[m]}", jobs=jobs, n_scalar=mp.n_scalar, n_out=mp.n_out,
             n_table=mp.n_table, runs=None if mp.owned_runs is None else np.array(mp.owned_runs, dtype=np.int64).reshape(-1, 2),
-            grad_range=mp.grad_range, sub_range=dict(mp.sub_range),
+            grad_range=mp.grad_range, sub_range=dict(mp.sub_range), node_threads=list(mp.node_threads),
         )
+
+    def _function_groups(self, mp: ModePlan, pi: int) -> list:
+        """Partition the phase's functions ``(family, index)`` that this mode stores something of
+        into at most ``node_groups`` groups of similar cost (operation count of the needed leaves),
+        largest first onto the lightest group.  One group (everything) unless asked otherwise."""
+        prog = mp.prog[pi]
+        p = self.lo.phases[pi]
+        fam = {"d": p.F_d, "I": p.F_I, "c": p.F_c}
+        cost: dict = {}
+        for lf in prog.need:
+            fn = fam[lf.key[0]][lf.key[1]]
+            e = fn.expr if lf.kind == "F" else (fn.G_expr if lf.kind == "G" else fn.H_expr)[lf.key[2]]
+            cost[(lf.key[0], lf.key[1])] = cost.get((lf.key[0], lf.key[1]), 0) + 1 + int(sp.count_ops(e))
+        k = max(1, min(int(self.node_groups), len(cost))) if not self.fused else 1
+        if k <= 1:
+            return [set(cost)]
+        groups, load = [set() for _ in range(k)], [0] * k
+        for fn_key, c in sorted(cost.items(), key=lambda kv: (-kv[1], kv[0])):
+            g = load.index(min(load))
+            groups[g].add(fn_key)
+            load[g] += c
+        return [g for g in groups if g] or [set()]
 
     def _node_kernel(self, mp: ModePlan, pi: int, kname: str) -> str:
         lo = self.lo
@@ -807,8 +846,22 @@ class DevicePlan:
         A("{")
         A(f"    const long long* T = pk_tab_{name};")
         A(f"    const int Lm = (int){T(col.L_m)};")
-        A("    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;")
-        A("    if (gid >= (long long)B * Lm) return;")
+        # expression groups (opt-in, DevicePlan(node_groups=k)): the functions of the phase are spread
+        # over up to k threads per node, each with the leaves (and the CSE) of its own functions only --
+        # "one thread per node per expression group".  Every store term carries leaves of exactly one
+        # function, so the stores split cleanly; group-major thread order keeps warps uniform.
+        fn_groups = self._function_groups(mp, pi)
+        G = len(fn_groups)
+        mp.node_threads[pi] = G
+        if G == 1:
+            A("    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;")
+            A("    if (gid >= (long long)B * Lm) return;")
+            A("    const int grp = 0;")
+        else:
+            A("    const long long gid0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;")
+            A(f"    if (gid0 >= (long long)B * Lm * {G}) return;")
+            A("    const int grp = (int)(gid0 / ((long long)B * Lm));")
+            A("    const long long gid = gid0 - (long long)grp * B * Lm;")
         A("    const int b = (int)(gid / Lm);")
         A("    const int c = (int)(gid - (long long)b * Lm);")
         A(f"    const double* xs = X + (long long)b * {T(lo.r_s)};")
@@ -866,65 +919,79 @@ class DevicePlan:
         for j, sym in enumerate(p.u):
             A(f"    const double u{j} = xp[{n_x}LL * Lx + {j}LL * Lm + c];")
             names[sym] = f"u{j}"
-        # function leaves needed by this mode, one CSE over all of them
+        # function leaves needed by this mode: one CSE per expression group
         fam = {"d": p.F_d, "I": p.F_I, "c": p.F_c}
-        leaves = []
-        for lf in sorted(prog.need, key=lambda l: (l.key[0], l.key[1], l.kind, l.key[2:] or (0,))):
-            fn = fam[lf.key[0]][lf.key[1]]
-            e = fn.expr if lf.kind == "F" else (fn.G_expr if lf.kind == "G" else fn.H_expr)[lf.key[2]]
-            leaves.append((_ident(lf), e))
-        if leaves:
-            L.append(emit_block(leaves, names, prefix="ce").rstrip("\n"))
         A("    const long long nd = (long long)b * Lm + c;")
 
-        def stores(nset, indent):
+        def group_of(code):
+            fn = _function_of(code)
+            for g, members in enumerate(fn_groups):
+                if fn in members:
+                    return g
+            return 0
+
+        def stores(nset, indent, grp):
             body = []
             for key, slot in prog.s_store.items():
-                if key[0] == nset:
+                if key[0] == nset and group_of(key[1]) == grp:
                     body.append(f"{indent}Sb[{T(slot)}] = {key[1]};")
             for key, row in prog.w_store.items():
-                if key[0] == nset:
+                if key[0] == nset and group_of(key[1]) == grp:
                     body.append(f"{indent}W[{T(('row', row))} + nd] = {key[1]};")
             for ns, code, dst, lam, c_lo in prog.direct:
-                if ns == nset:
+                if ns == nset and group_of(code) == grp:
                     e = f"c - {T(c_lo)}"
                     val = code if lam < 0 else f"{code} * lam[{T(lam)} + {e}]"
                     body.append(f"{indent}out[{T(dst)} + {e}] = {val};")
             return body
 
-        L += stores("all", "    ")
-        A("    if (first) {")
-        A(f"        Sb[{T(self.header[pi])}] = dt;")
-        for i in range(n_x):
-            A(f"        Sb[{T(self.header[pi] + 1 + i)}] = x{i};")
-        L += stores("basic", "        ")
-        L += stores("front", "        ")
-        if has_back:
-            A("    } else if (last) {")
-            L += stores("back", "        ")
-        A("    } else {")
-        L += stores("mid", "        ")
-        if prog.walks:
-            wt = self.walk_tables[pi]
-            A("        // fused expansion through the integration operator: this node's column of its")
-            A("        // interval block (two columns for a shared LGL border node), phasebase.py:1120-1124, 1280-1285")
-            A(f"        const int K = (int)IP[{T(wt['node_iv'])} + c];")
-            A(f"        const long long* rk = IP + {T(wt['rec'])} + 8LL * K;")
-            A("        const int cc = c - (int)rk[4];")
-            A(f"        const PkColumn col0 = pk_column(DP, rk, cc, DP[{T(wt['width'])} + K]);")
-            if wt["lgl"]:
-                A("        const bool shared = (cc == 0 && K > 0);")
-                A("        const long long* rj = shared ? rk - 8 : rk;")
-                A(f"        const PkColumn col1 = pk_column(DP, rj, (int)rj[0] - 1, DP[{T(wt['width'])} + (shared ? K - 1 : K)]);")
-            for code, dst, lam, sign in prog.walks:
-                lam0 = "nullptr" if lam < 0 else f"lam + {T(lam)}"
-                A(f"        {{ const double v = {code}; double* o = out + {T(dst)}; const double* lm = {lam0};")
-                A(f"          pk_walk(o, v, col0, lm, {sign!r});")
+        for grp, members in enumerate(fn_groups):
+            A(f"    if (grp == {grp}) {{")
+            leaves = []
+            for lf in sorted(prog.need, key=lambda l: (l.key[0], l.key[1], l.kind, l.key[2:] or (0,))):
+                if (lf.key[0], lf.key[1]) not in members:
+                    continue
+                fn = fam[lf.key[0]][lf.key[1]]
+                e = fn.expr if lf.kind == "F" else (fn.G_expr if lf.kind == "G" else fn.H_expr)[lf.key[2]]
+                leaves.append((_ident(lf), e))
+            if leaves:
+                L.append(emit_block(leaves, names, prefix=f"ce{grp}" if G > 1 else "ce").rstrip("\n"))
+            L += stores("all", "    ", grp)
+            A("    if (first) {")
+            if grp == 0:
+                A(f"        Sb[{T(self.header[pi])}] = dt;")
+                for i in range(n_x):
+                    A(f"        Sb[{T(self.header[pi] + 1 + i)}] = x{i};")
+            L += stores("basic", "        ", grp)
+            L += stores("front", "        ", grp)
+            if has_back:
+                A("    } else if (last) {")
+                L += stores("back", "        ", grp)
+            A("    } else {")
+            L += stores("mid", "        ", grp)
+            if prog.walks and grp == 0:
+                wt = self.walk_tables[pi]
+                A("        // fused expansion through the integration operator: this node's column of its")
+                A("        // interval block (two columns for a shared LGL border node), phasebase.py:1120-1124, 1280-1285")
+                A(f"        const int K = (int)IP[{T(wt['node_iv'])} + c];")
+                A(f"        const long long* rk = IP + {T(wt['rec'])} + 8LL * K;")
+                A("        const int cc = c - (int)rk[4];")
+                A(f"        const PkColumn col0 = pk_column(DP, rk, cc, DP[{T(wt['width'])} + K]);")
                 if wt["lgl"]:
-                    A(f"          if (shared) pk_walk(o, v, col1, lm, {sign!r}); }}")
-                else:
-                    A("        }")
-        A("    }")
+                    A("        const bool shared = (cc == 0 && K > 0);")
+                    A("        const long long* rj = shared ? rk - 8 : rk;")
+                    A(f"        const PkColumn col1 = pk_column(DP, rj, (int)rj[0] - 1, DP[{T(wt['width'])} + (shared ? K - 1 : K)]);")
+                for code, dst, lam, sign in prog.walks:
+                    lam0 = "nullptr" if lam < 0 else f"lam + {T(lam)}"
+                    A(f"        {{ const double v = {code}; double* o = out + {T(dst)}; const double* lm = {lam0};")
+                    A(f"          pk_walk(o, v, col0, lm, {sign!r});")
+                    if wt["lgl"]:
+                        A(f"          if (shared) pk_walk(o, v, col1, lm, {sign!r}); }}")
+                    else:
+                        A("        }")
+            A("    }")
+            A("    }")
+        A("    if (grp != 0) return;")
         A("    if (last) {")
         for i in range(n_x):
             if has_back:

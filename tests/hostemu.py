@@ -67,9 +67,9 @@ def _ptr(a):
 
 
 class HostEmu:
-    def __init__(self, system, batch=1, fixed=None, fused=False, shard=None):
+    def __init__(self, system, batch=1, fixed=None, fused=False, shard=None, node_groups=1):
         self.lo = system.lowering
-        self.dp = P.DevicePlan(self.lo, batch, fused=fused, shard=shard)
+        self.dp = P.DevicePlan(self.lo, batch, fused=fused, shard=shard, node_groups=node_groups)
         self.B = batch
         modes = range(6) if shard is None and not fused else range(5)  # + the fused set pipeline
         for m in modes:
@@ -103,7 +103,7 @@ class HostEmu:
             wm = self.dpool[dp.wm_off[pi] : dp.wm_off[pi] + Lm].copy()
             getattr(lib, "run_" + k)(
                 _ptr(X), _ptr(LAM), _ptr(FIX), _ptr(tm), _ptr(wm), _ptr(S), _ptr(W), _ptr(OUT),
-                ctypes.c_int(B), _ptr(self.dpool), _ptr(self.ipool), ctypes.c_longlong(B * Lm),
+                ctypes.c_int(B), _ptr(self.dpool), _ptr(self.ipool), ctypes.c_longlong(B * Lm * f["node_threads"][pi]),
             )
         jobs = f["jobs"]
         for jb in jobs[P.ST_REDUCE]:
