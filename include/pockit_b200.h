@@ -211,6 +211,9 @@ int pk_timeline(pk_engine *e, const int *modes, int n_modes, double *rows, int m
  * meshes [kernel pk_expand_cols] */
 int pk_expand_variant(pk_engine *e, int mode, int *variant);
 int pk_kernel_launches(pk_engine *e, int64_t *count);
+/* process-wide cache of NVRTC results keyed by (architecture, options, source): the generated
+ * programs take every mesh-dependent number from a table, so re-planning a re-meshed model compiles nothing */
+int pk_cubin_cache_stats(int64_t *hits, int64_t *misses);
 int pk_x_uploads(pk_engine *e, int64_t *count);       /* host-to-device copies of x so far */ /* kernels launched so far by this engine */
 int pk_flush_l2(pk_engine *e);                        /* overwrite a buffer larger than L2 */
 

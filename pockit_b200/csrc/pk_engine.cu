@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -282,10 +284,23 @@ static int compile(const pk_mode_desc* d, int device, std::vector<char>& cubin) 
   return compile_source(d->cuda_source, d->nvrtc_options, d->n_nvrtc_options, device, cubin);
 }
 
+// Process-wide cubin cache keyed by (architecture, options, source).  The generated programs read
+// every size and offset from a __constant__ table, so re-meshing a model (set_discretization ->
+// System.update(): a new engine) produces the same source and costs no NVRTC compilation.
+static std::mutex g_cache_mutex;
+static std::map<std::string, std::vector<char>> g_cubin_cache;
+static long long g_cache_hits = 0, g_cache_misses = 0;
+
+extern "C" int pk_cubin_cache_stats(int64_t* hits, int64_t* misses) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  if (hits) *hits = g_cache_hits;
+  if (misses) *misses = g_cache_misses;
+  return 0;
+}
+
+static int compile_uncached(const char* source, const std::vector<const char*>& opts, std::vector<char>& cubin);
+
 static int compile_source(const char* source, const char* const* extra, int n_extra, int device, std::vector<char>& cubin) {
-  nvrtcProgram prog;
-  if (nvrtcCreateProgram(&prog, source, "pockit_b200_generated.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
-    return fail("nvrtcCreateProgram failed");
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   // B200 is sm_100: compile for the arch-specific target; anything else gets its own real arch
@@ -298,6 +313,31 @@ static int compile_source(const char* source, const char* const* extra, int n_ex
     opts.push_back(extra[i]);
   }
   if (!fmad_given) opts.push_back("--fmad=false");
+  std::string key;
+  for (const char* o : opts) { key += o; key += '\n'; }
+  key += '\0';
+  key += source;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    auto it = g_cubin_cache.find(key);
+    if (it != g_cubin_cache.end()) {
+      cubin = it->second;
+      ++g_cache_hits;
+      return 0;
+    }
+  }
+  if (compile_uncached(source, opts, cubin)) return 1;
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  ++g_cache_misses;
+  if (g_cubin_cache.size() >= 64) g_cubin_cache.clear();  // bounded: a long sweep over models must not grow without limit
+  g_cubin_cache[key] = cubin;
+  return 0;
+}
+
+static int compile_uncached(const char* source, const std::vector<const char*>& opts, std::vector<char>& cubin) {
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, source, "pockit_b200_generated.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    return fail("nvrtcCreateProgram failed");
   nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   if (r != NVRTC_SUCCESS) {
     size_t n = 0;

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import plan as P
 
-__all__ = ["Engine", "load_library", "library_path", "PinnedArray"]
+__all__ = ["Engine", "load_library", "library_path", "PinnedArray", "cubin_cache_stats"]
 
 N_STAGES = 6
 N_MODES = 6  # five callbacks + the fused set pipeline (plan.SET)
@@ -112,6 +112,7 @@ def load_library():
         "pk_kernel_launches": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "pk_expand_variant": ([vp, C.c_int, C.POINTER(C.c_int)], C.c_int),
         "pk_x_uploads": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "pk_cubin_cache_stats": ([C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         "pk_timeline": ([vp, C.POINTER(C.c_int), C.c_int, vp, C.c_int, C.POINTER(C.c_int)], C.c_int),
         "pk_flush_l2": ([vp], C.c_int),
         "pk_alloc_host": ([C.c_size_t], vp),
@@ -146,6 +147,14 @@ class PinnedArray:
         if getattr(self, "_p", None):
             self._lib.pk_free_host(self._p)
             self._p = None
+
+
+def cubin_cache_stats() -> tuple:
+    """(hits, misses) of the library's process-wide NVRTC result cache."""
+    lib = load_library()
+    h, m = C.c_int64(), C.c_int64()
+    lib.pk_cubin_cache_stats(C.byref(h), C.byref(m))
+    return h.value, m.value
 
 
 class Engine:

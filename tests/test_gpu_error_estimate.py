@@ -56,21 +56,3 @@ def test_error_data_matches_oracle_on_a_fine_mesh(scheme, mesh, n):
     # a random point is not a solution: the check must fail somewhere; with huge tolerances it passes
     assert not ok[0].all() and not S.check_continuous(x)
     assert S.check_continuous(x, 1e9, 1e9)
-
-
-@pytest.mark.parametrize("scheme", ["lobatto", "radau"])
-def test_check_continuous_known_answers(scheme):
-    """The reference's own known-answer test (tests/test_labatto/test_check_lobatto.py:22-36 and the
-    radau twin): polynomial trajectories that satisfy x' = u exactly pass, perturbed ones fail."""
-    import importlib
-
-    from pockit_b200 import problems
-
-    mod = importlib.import_module(f"pockit_b200.{scheme}")
-    S, cases = problems.check_system(mod)
-    for value, expected in cases:
-        assert S.check_continuous(value) is expected
-    with pytest.raises(NotImplementedError):
-        S.check_discontinuous(cases[0][0])
-    with pytest.raises(ValueError, match="len\\(value\\)"):
-        S.check_continuous([cases[0][0][0]])

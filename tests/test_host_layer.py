@@ -155,3 +155,21 @@ def test_callbacks_need_the_cuda_engine(monkeypatch):
     monkeypatch.setenv("POCKIT_B200_LIB", "/nonexistent/libpockit_b200.so")
     with pytest.raises(RuntimeError):
         S.objective(np.zeros(S.L))
+
+
+def test_generated_source_does_not_depend_on_the_mesh():
+    """Sizes and offsets reach the per-node programs through a table, so re-meshing a model yields the
+    same CUDA source (the engine's cubin cache then compiles nothing)."""
+    import pockit_b200.radau as rad
+    from pockit_b200 import plan as P
+    from pockit_b200 import problems
+
+    def sources(S):
+        dp = P.DevicePlan(S.lowering)
+        for m in range(6):
+            dp.mode(m)
+        return [dp.finalize(m)["source"] for m in range(6)]
+
+    base = sources(problems.robot_arm(rad, 6, 20))
+    assert sources(problems.robot_arm(rad, 9, 7)) == base
+    assert sources(problems.robot_arm(rad, [0, 0.3, 0.5, 1.0], [4, 6, 5])) == base
