@@ -52,6 +52,10 @@ class CachedCallbacks:
         self.stats["points"] += 1
 
     def _call(self, modes, fct_c=None, fct_o=None):
+        # results land in the engine's page-locked buffers (device-to-host at full PCIe rate) and are
+        # copied out once into the fresh arrays the solver keeps -- faster than copying 100 MB from the
+        # device straight into pageable memory
+        self.engine.reuse_outputs = True
         res = self.engine.evaluate(None if self._resident else self._x, fct_c, fct_o, modes=list(modes))
         self._resident = True
         self.stats["engine_calls"] += 1
