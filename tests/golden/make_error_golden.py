@@ -27,6 +27,9 @@ CASES = {
     "humanoid_lgl_4x5": ("humanoid", "lobatto", {"mesh": 4, "num_point": 5}),
     "tiny_lgl_1x3": ("tiny", "lobatto", {"mesh": 1, "num_point": 3}),
     "tiny_lgr_1x2": ("tiny", "radau", {"mesh": 1, "num_point": 2}),
+    # hp-style meshes: mixed orders and widths
+    "rocket_lgl_hp": ("rocket", "lobatto", {"mesh": [0, 0.05, 0.2, 0.45, 0.5, 1.0], "num_point": [3, 6, 4, 2, 9]}),
+    "robot_arm_lgr_hp": ("robot_arm", "radau", {"mesh": [0, 0.3, 0.35, 0.7, 1.0], "num_point": [5, 2, 8, 3]}),
 }
 
 
