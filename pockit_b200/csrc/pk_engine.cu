@@ -42,6 +42,8 @@ struct ExpandGroup {
   long long* prefix = nullptr; long long blocks = 0; int uniform = 0; size_t smem = 0;
   // parameter-driven column kernel (same-order meshes, few jobs / lists)
   bool cols = false; PkXcParams xc; unsigned xc_gx = 0; size_t xc_smem = 0;
+  // bulk-store variant of it (opt-in): whole intervals per block, image handed to the TMA engine
+  bool bulk = false; int xb_per_block = 0; unsigned xb_gx = 0; size_t xb_smem = 0;
 };
 
 struct ModeState {
@@ -406,6 +408,7 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
   if (const char* env = getenv("POCKIT_B200_EXPAND")) {
     if (!strcmp(env, "params") && !cols) return fail("POCKIT_B200_EXPAND=params: jobs do not fit the parameter-driven kernel");
     if (!strcmp(env, "columns")) cols = false;
+    if (!strcmp(env, "bulk") && !cols) return fail("POCKIT_B200_EXPAND=bulk: jobs do not fit the parameter-driven kernel");
   }
   if (cols) {
     g.cols = true;
@@ -430,6 +433,20 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
     g.xc_gx = (unsigned)((max_pairs + PK_XC_THREADS - 1) / PK_XC_THREADS);
     auto kern = g.lam ? (const void*)pk_expand_cols<true> : (const void*)pk_expand_cols<false>;
     if (xsm > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+    if (const char* env = getenv("POCKIT_B200_EXPAND")) {
+      if (!strcmp(env, "bulk") && n0 <= PK_XB_THREADS) {  // TMA bulk-store variant, same parameters
+        const long long per = PK_XB_THREADS / n0, bn0 = n0 * r0;
+        const size_t bsm = sizeof(double) * (size_t)(((bn0 + 1) & ~1LL) + ((per * r0 + 1) & ~1LL) + per * bn0 + 2);
+        if (bsm <= 200 * 1024) {
+          g.bulk = true;
+          g.xb_per_block = (int)per;
+          g.xb_smem = bsm;
+          g.xb_gx = (unsigned)((max_pairs / n0 + per - 1) / per);
+          auto bk = g.lam ? (const void*)pk_expand_bulk<true> : (const void*)pk_expand_bulk<false>;
+          if (bsm > 48 * 1024) CK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        }
+      }
+    }
     return 0;
   }
   if (g.smem > 48 * 1024)
@@ -615,7 +632,13 @@ static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n +
 static void launch_expand(const ModeState& ms, const PkCtx& cx, int B, cudaStream_t st) {
   for (const ExpandGroup& g : ms.exp) {
     const pk_job* jobs = ms.jobs[PK_STAGE_EXPAND] + g.first;
-    if (g.cols) {
+    if (g.bulk) {
+      const dim3 grid(g.xb_gx, (unsigned)g.xc.n_lists, B);
+      if (g.lam)
+        pk_expand_bulk<true><<<grid, PK_XB_THREADS, g.xb_smem, st>>>(cx, g.xc, g.xb_per_block);
+      else
+        pk_expand_bulk<false><<<grid, PK_XB_THREADS, g.xb_smem, st>>>(cx, g.xc, g.xb_per_block);
+    } else if (g.cols) {
       const dim3 grid(g.xc_gx, (unsigned)g.xc.n_lists, B);
       if (g.lam)
         pk_expand_cols<true><<<grid, PK_XC_THREADS, g.xc_smem, st>>>(cx, g.xc);
@@ -1281,7 +1304,7 @@ extern "C" int pk_x_uploads(pk_engine* e, int64_t* count) {
 extern "C" int pk_expand_variant(pk_engine* e, int mode, int* variant) {
   if (!e || !variant || mode < 0 || mode >= PK_N_MODES) return fail("pk_expand_variant: bad argument");
   const ModeState& ms = e->mode[mode];
-  *variant = ms.exp.empty() ? 0 : (ms.exp.back().cols ? 2 : 1);
+  *variant = ms.exp.empty() ? 0 : (ms.exp.back().bulk ? 3 : (ms.exp.back().cols ? 2 : 1));
   return 0;
 }
 

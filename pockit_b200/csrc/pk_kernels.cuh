@@ -345,6 +345,83 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bulk-store variant of the parameter-driven column walk (opt-in, POCKIT_B200_EXPAND=bulk; written
+// after the round-1 GPU budget was spent, so it is compiled and SASS-checked but NOT yet run).
+// A block owns PK_XB_PAIRS / n WHOLE intervals of one list, i.e. one contiguous run of output slots.
+// Its threads compute the same values with the same association as pk_expand_cols, but store them
+// into a shared-memory image of that run; one thread then hands the image to the TMA engine as a
+// single 1-D bulk copy (cp.async.bulk.global.shared::cta): the LSU issues no global stores and the
+// run reaches L2 as whole sectors whatever the 8-byte alignment of the reference's slot offsets
+// (the image is placed in shared memory with the same 16-byte phase as its destination; an odd
+// first / last element is stored normally).
+#define PK_XB_THREADS 128
+template <bool LAM>
+__global__ void __launch_bounds__(PK_XB_THREADS) pk_expand_bulk(PkCtx cx, const __grid_constant__ PkXcParams prm, int per_block) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int n = prm.n, rows = prm.rows;
+  const int bn = n * rows;
+  double* u_s = smem_d;                               // [bn] sign-folded unit block
+  double* lam_s = u_s + ((bn + 1) & ~1);              // [per_block * rows]
+  double* img = lam_s + ((per_block * rows + 1) & ~1);  // [per_block * bn + 2], 16-byte aligned
+  const PkXcList& L = prm.list[blockIdx.y];
+  const PkXcJob& J = prm.job[L.job];
+  const int b = blockIdx.z;
+  const unsigned nK = J.pairs / (unsigned)n;
+  const unsigned K0 = blockIdx.x * (unsigned)per_block;
+  if (K0 >= nK) return;  // lists of a shorter job
+  const unsigned Kn = nK - K0 < (unsigned)per_block ? nK - K0 : (unsigned)per_block;  // intervals of this block
+  const unsigned t = threadIdx.x;
+  const bool live = t < Kn * (unsigned)n;
+  const unsigned kk = live ? t / (unsigned)n : 0;
+  const unsigned cc = live ? t - kk * (unsigned)n : 0;
+  const unsigned K = K0 + kk;
+  double sv = 0.0, w = 0.0;
+  if (live) {
+    sv = cx.W[L.wbase + (long long)b * J.Lm + J.node0 + (long long)K * J.step + cc];
+    w = cx.dpool[J.width + K];
+  }
+  {
+    const double* unit = cx.dpool + prm.unit;
+    for (int q = t; q < bn; q += PK_XB_THREADS) u_s[q] = prm.sign * unit[q];
+    if (LAM) {
+      const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K0 * rows;
+      for (int q = t; q < (int)Kn * rows; q += PK_XB_THREADS) lam_s[q] = lam[q];
+    }
+  }
+  double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + L.dst + (long long)K0 * bn;  // first slot of the run
+  const unsigned phase = (unsigned)(((unsigned long long)(size_t)out >> 3) & 1ull);  // 1: the run starts on an odd double
+  double* run = img + phase;  // image element j lives at run[j]: same 16-byte phase as out[j]
+  __syncthreads();
+  if (live) {
+    double* o = run + kk * (unsigned)bn + cc;
+    const double* u = u_s + cc;
+    const double* lm = lam_s + kk * (unsigned)rows;
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+      double v = (u[r * n] * w) / 2.0;
+      if (LAM) v = v * lm[r];
+      o[r * n] = v * sv;
+    }
+  }
+  // make the generic-proxy writes to shared memory visible to the async proxy, then let one thread copy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (t == 0) {
+    const unsigned total = Kn * (unsigned)bn;
+    unsigned j0 = phase;                    // first element on a 16-byte boundary
+    if (j0) out[0] = run[0];
+    unsigned cnt = (total - j0) & ~1u;      // whole 16-byte pairs
+    if (j0 + cnt < total) out[total - 1] = run[total - 1];
+    if (cnt) {
+      const unsigned src = (unsigned)__cvta_generic_to_shared(run + j0);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + j0), "r"(src), "r"(cnt * 8u) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the image must outlive the copy's reads
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double pk_list_at(const PkCtx& cx, const double* Sb, int b, int scalar, int unit,
                                              long long src, long long lm, long long c_lo, long long k) {
   if (unit) return 1.0;

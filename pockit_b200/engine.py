@@ -510,7 +510,7 @@ class Engine:
         self.load(mode)
         v = C.c_int()
         self._check(self.lib.pk_expand_variant(self._h, mode, C.byref(v)))
-        return {0: "", 1: "pk_expand_blocks", 2: "pk_expand_cols"}[v.value]
+        return {0: "", 1: "pk_expand_blocks", 2: "pk_expand_cols", 3: "pk_expand_bulk"}[v.value]
 
     def flush_l2(self):
         self._check(self.lib.pk_flush_l2(self._h))
