@@ -278,21 +278,46 @@ class ModePlan:
             generic.append(r)
             runs.append((dst + e0, e1 - e0))
         self.jobs[ST_GENERIC] = generic
-        expand = []
+        # Block expansions: the (list, interval) tiles of all jobs, in output order (list-major), are
+        # dealt out as ONE contiguous range per rank, weighted by tile size.  A rank then owns a few
+        # whole lists plus at most two partial ones -- long contiguous runs, i.e. few large
+        # device-to-host copies (splitting every list by interval range instead gave ~70 copies of
+        # 1.6 MB per rank and set at 4 GPUs).
+        tiles = []  # (job record, list index, intervals, slots per tile)
         for rec in self.jobs[ST_EXPAND]:
             n, rows = rec["i"][3], rec["i"][4]
-            Ka, Kb = part(rec["i"][11] // n)
-            if Kb == Ka:
+            for li in range(len(rec["lists"])):
+                tiles.append((rec, li, rec["i"][11] // n, n * rows))
+        total = sum(nK * sz for _, _, nK, sz in tiles)
+        lo_w, hi_w = total * g // G, total * (g + 1) // G
+        expand, seen = [], 0
+        groups: dict = {}  # (id(job record), Ka, Kb) -> cloned record holding the lists with that range
+        for rec, li, nK, sz in tiles:
+            first, last = seen, seen + nK * sz
+            seen = last
+            a, b = max(first, lo_w), min(last, hi_w)
+            if b <= a:
                 continue
-            r = clone(rec)
-            r["i"][11] = (Kb - Ka) * n
-            r["i"][6] += Ka * rec["i"][5]
-            r["i"][8] += Ka
-            if rec["i"][2] >= 0:
-                r["i"][2] += Ka * rows
-            r["lists"] = [(dst + Ka * n * rows, row) for dst, row in rec["lists"]]
-            runs += [(dst, (Kb - Ka) * n * rows) for dst, _ in r["lists"]]
-            expand.append(r)
+            # whole tiles only: a tile belongs to the rank its first slot falls to
+            Ka, Kb = -(-(a - first) // sz), -(-(b - first) // sz)
+            if Kb <= Ka:
+                continue
+            n, rows = rec["i"][3], rec["i"][4]
+            key = (id(rec), Ka, Kb)
+            r = groups.get(key)
+            if r is None:
+                r = clone(rec)
+                r["i"][11] = (Kb - Ka) * n
+                r["i"][6] += Ka * rec["i"][5]
+                r["i"][8] += Ka
+                if rec["i"][2] >= 0:
+                    r["i"][2] += Ka * rows
+                r["lists"] = []
+                groups[key] = r
+                expand.append(r)
+            dst, row = rec["lists"][li]
+            r["lists"].append((dst + Ka * n * rows, row))
+            runs.append((dst + Ka * n * rows, (Kb - Ka) * n * rows))
         self.jobs[ST_EXPAND] = expand
         # runs the (replicated) per-node programs write themselves: split ownership of the copy only
         for pi, prog in enumerate(self.prog):
