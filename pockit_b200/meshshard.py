@@ -9,9 +9,10 @@ expansion and the copy -- and replicates what is cheap:
   robot_arm LGR 2000x20) and runs the per-node programs, the quadrature sums and the system
   program for all nodes: a few microseconds, and it makes the integrals bit-identical on every
   rank without an all-reduce -- the data path has **no collective**;
-* rank ``g`` runs the block expansion for the intervals ``[nK g / G, nK (g+1) / G)`` of every list
-  and its share of the long table / constant runs (``plan.ModePlan._shard``), and copies exactly
-  those slot runs over *its own* PCIe link into a host buffer shared by all ranks
+* rank ``g`` runs the block expansion for one contiguous range of the (list, interval) tiles in
+  output order -- a few whole lists plus at most two partial ones -- and its share of the long
+  table / constant runs (``plan.ModePlan._shard``), and copies exactly those slot runs (a handful of
+  long ones) over *its own* PCIe link into a host buffer shared by all ranks
   (a ``/dev/shm`` mapping, page-locked in every process), at the offsets of the reference pattern;
 * rank 0 is the caller: it owns the small callbacks (objective, gradient, constraints), publishes
   ``x`` in the shared mapping, evaluates its own share and waits for the others' completion flags.
