@@ -802,6 +802,19 @@ extern "C" int pk_upload_x(pk_engine* e, const double* x) {
   if (!e || !x) return fail("pk_upload_x: null argument");
   CK(cudaSetDevice(e->device));
   const size_t n = sizeof(double) * (size_t)e->dims.batch * (size_t)e->dims.L;
+  // x already in page-locked memory (pk_alloc_host, or a range registered with pk_host_register such as
+  // the mapping the ranks of a sharded mesh share): copy straight from it.  The caller must leave it
+  // alone until the evaluation that uses it returns (every pk_eval_* synchronises before returning).
+  cudaPointerAttributes at;
+  const bool locked = cudaPointerGetAttributes(&at, x) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  if (!locked) (void)cudaGetLastError();
+  if (locked) {
+    CK(cudaMemcpyAsync(e->X, x, n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaEventRecord(e->x_done, e->stream));
+    e->x_resident = true;
+    ++e->x_uploads;
+    return 0;
+  }
   CK(cudaEventSynchronize(e->x_done));  // the previous copy may still be reading the staging buffer
   memcpy(e->hX, x, n);
   CK(cudaMemcpyAsync(e->X, e->hX, n, cudaMemcpyHostToDevice, e->stream));
