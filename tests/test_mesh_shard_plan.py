@@ -25,8 +25,7 @@ def _assemble(S, G, mode, x, lam=None, sigma=None):
     return full, cover
 
 
-@pytest.mark.parametrize("split_min", [4, 1024])
-@pytest.mark.parametrize("G", [2, 3, 8])
+@pytest.mark.parametrize("G,split_min", [(2, 4), (3, 4), (8, 1024)])  # small runs split too / production threshold
 @pytest.mark.parametrize("case", ["robot_arm_lgr_6x20", "rocket_lgl_4x5", "quadrotor_lgl_14x6", "general_lgl", "general_lgr", "tiny_lgl_2x2"])
 def test_shards_partition_and_reassemble(case, G, split_min, monkeypatch):
     monkeypatch.setattr(P, "SPLIT_MIN", split_min)

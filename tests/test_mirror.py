@@ -27,15 +27,15 @@ def _reference(scheme):
 
 import os
 
-# the reference JIT-compiles every function with Numba (tens of seconds per model): three models by
+# the reference JIT-compiles every function with Numba (tens of seconds per model): two models by
 # default, the rest with POCKIT_B200_SLOW_TESTS=1
 CASES = [
     ("general", "lobatto", {}),
-    ("rocket", "lobatto", {"mesh": 3, "num_point": 4}),
     ("lqr", "radau", {"mesh": 3, "num_point": 4}),
 ]
 if os.environ.get("POCKIT_B200_SLOW_TESTS") == "1":
     CASES += [
+        ("rocket", "lobatto", {"mesh": 3, "num_point": 4}),
         ("general", "radau", {}),
         ("robot_arm", "radau", {"mesh": 4, "num_point": 5}),
         ("quadrotor", "lobatto", {"mesh": 4, "num_point": 4}),
