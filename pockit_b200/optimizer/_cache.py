@@ -35,6 +35,7 @@ class CachedCallbacks:
         self.grouping = grouping
         self._x = None
         self._resident = False
+        self._uploads = -1
         self._have: dict = {}
         self.stats = {"points": 0, "engine_calls": 0, "hits": 0}
 
@@ -56,8 +57,13 @@ class CachedCallbacks:
         # copied out once into the fresh arrays the solver keeps -- faster than copying 100 MB from the
         # device straight into pageable memory
         self.engine.reuse_outputs = True
-        res = self.engine.evaluate(None if self._resident else self._x, fct_c, fct_o, modes=list(modes))
+        # The device copy of x is shared with every other entry point of the engine (System.objective,
+        # System.evaluate, check_continuous, Engine.upload ...): residency is only trusted while the
+        # engine's upload counter still reads what it read right after this cache's own upload.
+        resident = self._resident and self.engine.x_uploads == self._uploads
+        res = self.engine.evaluate(None if resident else self._x, fct_c, fct_o, modes=list(modes))
         self._resident = True
+        self._uploads = self.engine.x_uploads
         self.stats["engine_calls"] += 1
         return res
 

@@ -585,6 +585,11 @@ class SystemLowering:
         out = []
         for pi, nset, e in self.integral_lists[j][0]:
             cnt = self._mid_count(pi, nset)
+            if cnt == 0:
+                # a phase without middle nodes (one interval of minimal order): the list is empty and
+                # contributes no slots whatever it is paired with (the reference reads a_i[0] of the
+                # empty array here, easyderiv.py:333, and then emits zero-length index arrays)
+                continue
             out.append(SysList(self._gidx(pi, e.base, e.stride, cnt), cnt, pi, nset, e.val))
         return out
 

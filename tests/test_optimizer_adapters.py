@@ -20,11 +20,16 @@ class EmuEngine:
         self.compacted = set()
         self.calls = []
         self.x = None
+        self.x_uploads = 0
+
+    def upload(self, x):  # any other entry point of the engine that replaces the resident x
+        self.x = np.array(x, copy=True)
+        self.x_uploads += 1
 
     def evaluate(self, x, fct_c=None, fct_o=None, modes=None, outs=None):
         self.calls.append((x is not None, tuple(modes)))
         if x is not None:
-            self.x = np.array(x, copy=True)
+            self.upload(x)
         res = {}
         for m in modes:
             v = self.e.run(m, self.x, fct_c, None if fct_o is None else float(np.asarray(fct_o).reshape(-1)[0]))
@@ -72,6 +77,24 @@ def test_cache_groups_callbacks_and_uploads_once_per_point():
     np.testing.assert_allclose(cb.hessian_c(x, lam), g["hessian"][n_o:], rtol=1e-12, atol=1e-14)
     # attribute passthrough (bounds / structures are the system's own)
     assert cb.L == S.L and np.array_equal(cb.jacobianstructure()[0], S.jacobianstructure()[0])
+
+
+def test_cache_notices_a_foreign_upload():
+    """The device copy of x belongs to the engine, not to the cache: when anything else uploads a
+    point in between (System.objective, check_continuous, Engine.upload ...), the next cached
+    callback at the old point must send x again instead of evaluating at the foreign one."""
+    S, g = build("robot_arm_lgr_6x20"), load("robot_arm_lgr_6x20")
+    F = FakeSystem(S)
+    cb = CachedCallbacks(F)
+    x = g["x"]
+    cb.objective(x)
+    F.engine.upload(x + 0.25)  # e.g. an `intermediate` hook calling system.check_continuous(x_k)
+    J = cb.jacobian(x)
+    assert F.engine.calls[-1] == (True, (P.GRAD, P.JAC))
+    np.testing.assert_allclose(J, g["jacobian"], rtol=1e-12, atol=1e-14)
+    H = cb.hessian(x, g["lam"], float(g["sigma"]))  # nothing in between: resident again
+    assert F.engine.calls[-1] == (False, (P.HESS,))
+    np.testing.assert_allclose(H, g["hessian"], rtol=1e-12, atol=1e-14)
 
 
 def test_cache_without_grouping_and_nan_points():

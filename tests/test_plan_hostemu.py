@@ -39,3 +39,32 @@ def test_fused_expansion_variant_matches_reference(name):
     x, lam, sigma = g["x"], g["lam"], float(g["sigma"])
     assert_close(E.run(P.JAC, x), g["jacobian"], "jacobian")
     assert_close(E.run(P.HESS, x, lam, sigma), g["hessian"], "hessian")
+
+
+@pytest.mark.parametrize("scheme,kw", [("lobatto", dict(mesh=1, num_point=2)), ("radau", dict(mesh=1, num_point=1))])
+def test_phase_without_middle_nodes_lowers_and_evaluates(scheme, kw):
+    """One interval of minimal order: no middle nodes, so every middle list is empty.  The reference is
+    not a parity target here -- its structures and values disagree in length on this mesh and
+    ``gradient`` raises (``easyderiv.py:333`` reads element 0 of empty arrays) -- but the lowering must
+    not fail, and values, structures and the plan must agree with each other."""
+    import importlib
+
+    from pockit_b200 import plan as P
+    from pockit_b200 import problems
+
+    S = problems.general(importlib.import_module(f"pockit_b200.{scheme}"), **kw)
+    x, lam, sigma = problems.evaluation_point(S, seed=3)
+    E = HostEmu(S)
+    jr, jc = S.jacobianstructure()
+    hr, hc = S.hessianstructure()
+    J, H = E.run(P.JAC, x), E.run(P.HESS, x, lam, sigma)
+    assert len(J) == len(jr) == len(jc) and len(H) == len(hr) == len(hc)
+    assert np.all(np.isfinite(J)) and np.all(np.isfinite(H)) and np.all(hr >= hc)
+    assert len(E.run(P.GRAD, x)) == S.L and len(E.run(P.CONS, x)) == len(S.c_lb)
+    # the Jacobian is still the derivative of the constraints
+    d = np.random.default_rng(0).normal(size=S.L)
+    eps = 1e-6
+    fd = (E.run(P.CONS, x + eps * d) - E.run(P.CONS, x - eps * d)) / (2 * eps)
+    jd = np.zeros(len(S.c_lb))
+    np.add.at(jd, jr, J * d[jc])
+    np.testing.assert_allclose(jd, fd, rtol=1e-5, atol=1e-6)
