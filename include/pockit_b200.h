@@ -195,10 +195,20 @@ int pk_run(pk_engine *e, int mode);               /* enqueue the mode's kernels 
 int pk_run_set(pk_engine *e, const int *modes, int n_modes);
 int pk_sync(pk_engine *e);
 int pk_download(pk_engine *e, int mode, double *out);
+/* `count` values from slot `offset` of every instance, packed [B][count]: hessian_o / hessian_c
+ * (systembase.py:735, 786) are the head / tail of the Hessian values -- one evaluation, only the
+ * requested part crosses PCIe */
+int pk_download_range(pk_engine *e, int mode, int64_t offset, int64_t count, double *out);
+/* device address ([B][n_out] doubles) and total count of a mode's result, for device-side consumers
+ * (e.g. an NCCL all-gather of instance-sharded batches) */
+int pk_out_device_pointer(pk_engine *e, int mode, void **ptr, int64_t *count);
 /* time `iters` back-to-back runs with CUDA events on the engine stream; ms_total covers the
  * whole mode, ms_stage[s] the kernels of each stage (s = 0..PK_N_STAGES-1 jobs, PK_N_STAGES = node
  * programs, PK_N_STAGES+1 = system program), measured in separate passes. */
 int pk_time(pk_engine *e, int mode, int iters, float *ms_total, float *ms_stage /* [PK_N_STAGES+2] */);
+/* one stage (bit s of stage_mask, as in pk_time) launch by launch, L2 flushed (untimed) before each:
+ * the dominant kernel under the cache conditions of the whole-set measurement */
+int pk_time_stage(pk_engine *e, int mode, unsigned stage_mask, int iters, int flush_l2, float *ms_each);
 /* device-resident throughput: `steps` times { [flush L2, untimed]; event; pk_run_set(modes); event };
  * ms_steps[s] is the CUDA-event time of step s on the engine stream */
 int pk_time_steps(pk_engine *e, const int *modes, int n_modes, int steps, int flush_l2, float *ms_steps);

@@ -34,6 +34,16 @@ static int fail(const std::string& msg) {
                   std::to_string(__LINE__) + ")");                                                 \
   } while (0)
 
+// timing event that is destroyed on every return path
+struct ScopedEvent {
+  cudaEvent_t ev = nullptr;
+  cudaError_t create() { return cudaEventCreate(&ev); }
+  ~ScopedEvent() {
+    if (ev) cudaEventDestroy(ev);
+  }
+  operator cudaEvent_t() const { return ev; }
+};
+
 // one launch of the block expansion: jobs [first, first + count) of the mode's EXPAND stage
 struct ExpandGroup {
   long long first = 0, count = 0;
@@ -58,6 +68,7 @@ struct ModeState {
   double *S = nullptr, *W = nullptr;  // scalar / node tables of this mode (modes may run concurrently)
   cudaStream_t stream = nullptr;      // used when a whole evaluation set is launched at once
   cudaEvent_t done = nullptr;
+  cudaEvent_t node_done = nullptr;    // recorded behind the per-node programs when a set is staggered (run_set)
   cudaStream_t side = nullptr;        // the small slot runs overlap the block expansion
   cudaEvent_t side_fork = nullptr, side_join = nullptr;
   // two more branches of the small-kernel DAG (defects / gradient gather run beside the reduction chain)
@@ -119,6 +130,7 @@ struct pk_engine {
   cudaEvent_t chain_ev[PK_N_MODES] = {};
   int chain_last = -1;
   bool chain = false;
+  bool stagger = false;  // set capture: record node_done behind every mode's per-node programs
 };
 
 // tag: job stage 0..5, 6 node programs, 7 system program, 8 compaction; edge 0 = before, 1 = after
@@ -160,6 +172,9 @@ extern "C" int pk_host_unregister(void* p) {
   return 0;
 }
 
+static int engine_allocate(pk_engine* e);
+extern "C" int pk_engine_destroy(pk_engine* e);
+
 extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   if (!d || !out) return fail("pk_engine_create: null argument");
   if (d->abi_version != PK_ABI_VERSION) return fail("pk_engine_create: ABI version mismatch");
@@ -171,6 +186,18 @@ extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   pk_engine* e = new pk_engine();
   e->dims = *d;
   e->device = device;
+  if (engine_allocate(e)) {  // release whatever was allocated before the failure
+    const std::string why = g_err;
+    pk_engine_destroy(e);
+    g_err = why;
+    return 1;
+  }
+  *out = e;
+  return 0;
+}
+
+static int engine_allocate(pk_engine* e) {
+  const pk_dims* d = &e->dims;
   const long long B = d->batch;
   long long n_out = d->L;
   if (d->m > n_out) n_out = d->m;
@@ -194,7 +221,6 @@ extern "C" int pk_engine_create(const pk_dims* d, int device, pk_engine** out) {
   CK(cudaMallocHost((void**)&e->hLAM, sizeof(double) * (size_t)(B * d->m > 0 ? B * d->m : 1)));
   CK(cudaMallocHost((void**)&e->hSIG, sizeof(double) * (size_t)B));
   CK(cudaStreamSynchronize(e->stream));
-  *out = e;
   return 0;
 }
 
@@ -213,6 +239,7 @@ static void free_mode(ModeState& ms) {
   if (ms.W) cudaFree(ms.W);
   if (ms.stream) cudaStreamDestroy(ms.stream);
   if (ms.done) cudaEventDestroy(ms.done);
+  if (ms.node_done) cudaEventDestroy(ms.node_done);
   if (ms.side) cudaStreamDestroy(ms.side);
   if (ms.side_fork) cudaEventDestroy(ms.side_fork);
   if (ms.side_join) cudaEventDestroy(ms.side_join);
@@ -535,6 +562,7 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     const bool big = mode == PK_MODE_JACOBIAN || mode == PK_MODE_HESSIAN || mode == PK_MODE_SET;
     CK(cudaStreamCreateWithPriority(&ms.stream, cudaStreamNonBlocking, use_prio && !big ? prio_hi : prio_lo));
     CK(cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ms.node_done, cudaEventDisableTiming));
     CK(cudaStreamCreateWithPriority(&ms.side, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaEventCreateWithFlags(&ms.side_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ms.side_join, cudaEventDisableTiming));
@@ -674,6 +702,7 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
       CK(cudaLaunchKernel((void*)ms.node_kernels[p], dim3(blocks_for(threads, 128)), dim3(128), args, 0, st));
       ++e->launches;
     }
+    if (e->stagger) CK(cudaEventRecord(ms.node_done, st));
     tr(e, mode, 6, 1, st);
   }
   // Dependencies after the per-node programs (N):
@@ -888,6 +917,35 @@ extern "C" int pk_download(pk_engine* e, int mode, double* out) {
   return 0;
 }
 
+// Part of a mode's result: `count` values from slot `offset` of every instance, packed [B][count].
+// hessian_o / hessian_c (systembase.py:735, 786) are the head / tail of the Hessian values: the engine
+// evaluates the mode once and only the requested part crosses PCIe.
+extern "C" int pk_download_range(pk_engine* e, int mode, int64_t offset, int64_t count, double* out) {
+  if (!e || !out || mode < 0 || mode >= PK_N_MODES) return fail("pk_download_range: bad argument");
+  ModeState& ms = e->mode[mode];
+  if (!ms.loaded) return fail("pk_download_range: mode not loaded");
+  if (ms.n_compact || !ms.dl_runs.empty() || ms.in_set) return fail("pk_download_range: not available with shaped outputs");
+  if (offset < 0 || count < 0 || offset + count > ms.n_out) return fail("pk_download_range: range outside the output");
+  CK(cudaSetDevice(e->device));
+  if (count)
+    CK(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)count, ms.OUT + offset, sizeof(double) * (size_t)ms.n_out,
+                         sizeof(double) * (size_t)count, (size_t)e->dims.batch, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// Device address of a mode's result buffer ([B][n_out] doubles, or the compacted values): lets a
+// caller hand the values to a collective (NCCL all-gather of sharded batches) without a host round trip.
+extern "C" int pk_out_device_pointer(pk_engine* e, int mode, void** ptr, int64_t* count) {
+  if (!e || !ptr || mode < 0 || mode >= PK_N_MODES) return fail("pk_out_device_pointer: bad argument");
+  ModeState& ms = e->mode[mode];
+  if (!ms.loaded) return fail("pk_out_device_pointer: mode not loaded");
+  if (ms.in_set) return fail("pk_out_device_pointer: the latest values live in the set pipeline's combined output");
+  *ptr = ms.n_compact ? (void*)ms.OUTC : (void*)ms.OUT;
+  if (count) *count = (ms.n_compact ? ms.n_compact : ms.n_out) * (int64_t)e->dims.batch;
+  return 0;
+}
+
 extern "C" int pk_engine_set_output_runs(pk_engine* e, int mode, const int64_t* runs, int64_t n_runs) {
   if (!e || mode < 0 || mode >= PK_N_MODES || n_runs < 0 || (n_runs && !runs)) return fail("pk_engine_set_output_runs: bad argument");
   ModeState& ms = e->mode[mode];
@@ -1026,9 +1084,9 @@ extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, con
 extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float* ms_stage) {
   if (!e || mode < 0 || mode >= PK_N_MODES || iters < 1) return fail("pk_time: bad argument");
   CK(cudaSetDevice(e->device));
-  cudaEvent_t a, b;
-  CK(cudaEventCreate(&a));
-  CK(cudaEventCreate(&b));
+  ScopedEvent a, b;
+  CK(a.create());
+  CK(b.create());
   auto timed = [&](unsigned mask, float* out) -> int {
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventRecord(a, e->stream));
@@ -1047,8 +1105,26 @@ extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float
       if (s == PK_STAGE_GRAD_SCALAR) { ms_stage[s] = 0.f; continue; }
       if (timed(mask, &ms_stage[s])) return 1;
     }
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
+  return 0;
+}
+
+// One stage of a mode timed launch by launch with the L2 flushed (untimed) before every launch: the
+// roofline figure of the dominant kernel is taken under the same cache conditions as the whole-set
+// throughput.  stage_mask as in launch_mode; ms_each[i] = CUDA-event time of launch i on the engine stream.
+extern "C" int pk_time_stage(pk_engine* e, int mode, unsigned stage_mask, int iters, int flush_l2, float* ms_each) {
+  if (!e || mode < 0 || mode >= PK_N_MODES || iters < 1 || !ms_each) return fail("pk_time_stage: bad argument");
+  CK(cudaSetDevice(e->device));
+  ScopedEvent a, b;
+  CK(a.create());
+  CK(b.create());
+  for (int i = 0; i < iters; ++i) {
+    if (flush_l2 && pk_flush_l2(e)) return 1;
+    CK(cudaEventRecord(a, e->stream));
+    if (launch_mode(e, mode, stage_mask, e->stream)) return 1;
+    CK(cudaEventRecord(b, e->stream));
+    CK(cudaEventSynchronize(b));
+    CK(cudaEventElapsedTime(&ms_each[i], a, b));
+  }
   return 0;
 }
 
@@ -1087,20 +1163,55 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     CK(cudaEventRecord(e->fork, e->stream));
     int rc = 0;
-    std::vector<int> order(want);  // largest outputs first: their expansions head the chain
-    for (int a = 1; a < n_modes; ++a)
-      for (int b = a; b > 0 && e->mode[order[b]].n_out > e->mode[order[b - 1]].n_out; --b) std::swap(order[b], order[b - 1]);
+    // Schedule of a set.  Every kernel of it either fills the machine on its own (the HBM-bound block
+    // expansions; on wide models also the per-node programs) or is a short link of a latency-bound
+    // chain, so what is released together merely shares the SMs and everything finishes late.  The
+    // critical path is  node program -> expansion  of the modes that have one (Jacobian, Hessian) with
+    // the expansions chained; it gets the machine first:
+    //   1. the per-node program of the first expansion mode runs alone, its expansion starts right behind;
+    //   2. the next expansion mode's per-node program is released when the previous one has finished
+    //      (it overlaps the running, HBM-bound expansion) -- its expansion follows the chain;
+    //   3. the small callbacks (objective, gradient, constraints) are released behind the last of those
+    //      per-node programs (POCKIT_B200_STAGGER=1: behind the first) and hide under the expansions.
+    // POCKIT_B200_STAGGER=0: everything is released at once (the round-1 schedule, largest first).
+    const char* sg = getenv("POCKIT_B200_STAGGER");
+    const int stagger = sg ? atoi(sg) : 2;
+    std::vector<int> order;
+    if (stagger > 0) {
+      std::vector<int> big, small;
+      for (int m : want) (e->mode[m].exp.empty() ? small : big).push_back(m);
+      for (size_t a = 1; a < big.size(); ++a)  // lighter mode first: its expansion heads the chain
+        for (size_t b = a; b > 0 && e->mode[big[b]].n_out < e->mode[big[b - 1]].n_out; --b) std::swap(big[b], big[b - 1]);
+      for (size_t a = 1; a < small.size(); ++a)
+        for (size_t b = a; b > 0 && e->mode[small[b]].n_out > e->mode[small[b - 1]].n_out; --b) std::swap(small[b], small[b - 1]);
+      order = big;
+      order.insert(order.end(), small.begin(), small.end());
+    } else {
+      order = want;  // largest outputs first: their expansions head the chain
+      for (int a = 1; a < n_modes; ++a)
+        for (int b = a; b > 0 && e->mode[order[b]].n_out > e->mode[order[b - 1]].n_out; --b) std::swap(order[b], order[b - 1]);
+    }
     const char* ch = getenv("POCKIT_B200_CHAIN");
     e->chain = !(ch && ch[0] == '0');
     e->chain_last = -1;
+    e->stagger = stagger > 0;
+    cudaEvent_t gate = nullptr, first_gate = nullptr;
     for (int k = 0; k < n_modes && !rc; ++k) {
       ModeState& ms = e->mode[order[k]];
+      const bool big = !ms.exp.empty();
       if (cudaStreamWaitEvent(ms.stream, e->fork, 0) != cudaSuccess) rc = 1;
+      cudaEvent_t wait_for = (stagger == 1 && !big) ? first_gate : gate;
+      if (!rc && stagger > 0 && wait_for && cudaStreamWaitEvent(ms.stream, wait_for, 0) != cudaSuccess) rc = 1;
       if (!rc) rc = launch_mode(e, order[k], ~0u, ms.stream);
+      if (big && !ms.node_kernels.empty()) {
+        gate = ms.node_done;
+        if (!first_gate) first_gate = gate;
+      }
       if (!rc && cudaEventRecord(ms.done, ms.stream) != cudaSuccess) rc = 1;
       if (!rc && cudaStreamWaitEvent(e->stream, ms.done, 0) != cudaSuccess) rc = 1;
     }
     e->chain = false;
+    e->stagger = false;
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     if (rc || ce != cudaSuccess || !graph) {
       if (graph) cudaGraphDestroy(graph);
@@ -1160,9 +1271,9 @@ extern "C" int pk_run_set(pk_engine* e, const int* modes, int n_modes) {
 extern "C" int pk_time_steps(pk_engine* e, const int* modes, int n_modes, int steps, int flush_l2, float* ms_steps) {
   if (!e || !modes || n_modes < 1 || steps < 1 || !ms_steps) return fail("pk_time_steps: bad argument");
   CK(cudaSetDevice(e->device));
-  cudaEvent_t a, b;
-  CK(cudaEventCreate(&a));
-  CK(cudaEventCreate(&b));
+  ScopedEvent a, b;
+  CK(a.create());
+  CK(b.create());
   for (int s = 0; s < steps; ++s) {
     if (flush_l2 && pk_flush_l2(e)) return 1;
     CK(cudaEventRecord(a, e->stream));
@@ -1171,8 +1282,6 @@ extern "C" int pk_time_steps(pk_engine* e, const int* modes, int n_modes, int st
     CK(cudaEventSynchronize(b));
     CK(cudaEventElapsedTime(&ms_steps[s], a, b));
   }
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
   return 0;
 }
 
@@ -1185,10 +1294,17 @@ extern "C" int pk_timeline(pk_engine* e, const int* modes, int n_modes, double* 
   CK(cudaSetDevice(e->device));
   for (int k = 0; k < n_modes; ++k)
     if (modes[k] < 0 || modes[k] >= PK_N_MODES || !e->mode[modes[k]].loaded) return fail("pk_timeline: mode not loaded");
-  std::vector<pk_engine::Mark> marks;
-  cudaEvent_t base, end;
-  CK(cudaEventCreate(&base));
-  CK(cudaEventCreate(&end));
+  struct Marks {  // the trace events are released on every return path
+    std::vector<pk_engine::Mark> v;
+    ~Marks() {
+      for (auto& mk : v)
+        if (mk.ev) cudaEventDestroy(mk.ev);
+    }
+  } owned;
+  std::vector<pk_engine::Mark>& marks = owned.v;
+  ScopedEvent base, end;
+  CK(base.create());
+  CK(end.create());
   CK(cudaStreamSynchronize(e->stream));
   for (int k = 0; k < 4; ++k)
     if (pk_flush_l2(e)) return 1;
@@ -1215,7 +1331,6 @@ extern "C" int pk_timeline(pk_engine* e, const int* modes, int n_modes, double* 
       rows[4 * n] = mk.mode; rows[4 * n + 1] = mk.tag; rows[4 * n + 2] = mk.edge; rows[4 * n + 3] = 1000.0 * ms_;
       ++n;
     }
-    cudaEventDestroy(mk.ev);
   }
   float tot = 0.f;
   cudaEventElapsedTime(&tot, base, end);
@@ -1224,8 +1339,6 @@ extern "C" int pk_timeline(pk_engine* e, const int* modes, int n_modes, double* 
     ++n;
   }
   *n_rows = n;
-  cudaEventDestroy(base);
-  cudaEventDestroy(end);
   return 0;
 }
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from pathlib import Path
 from typing import Optional
 
@@ -15,7 +16,7 @@ import numpy as np
 
 from . import plan as P
 
-__all__ = ["Engine", "load_library", "library_path", "PinnedArray", "cubin_cache_stats"]
+__all__ = ["Engine", "load_library", "library_path", "PinnedArray", "PinnedPool", "cubin_cache_stats"]
 
 N_STAGES = 6
 N_MODES = 6  # five callbacks + the fused set pipeline (plan.SET)
@@ -107,7 +108,10 @@ def load_library():
         "pk_run_set": ([vp, C.POINTER(C.c_int), C.c_int], C.c_int),
         "pk_sync": ([vp], C.c_int),
         "pk_download": ([vp, C.c_int, vp], C.c_int),
+        "pk_download_range": ([vp, C.c_int, C.c_int64, C.c_int64, vp], C.c_int),
+        "pk_out_device_pointer": ([vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)], C.c_int),
         "pk_time": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
+        "pk_time_stage": ([vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "pk_time_steps": ([vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "pk_kernel_launches": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "pk_expand_variant": ([vp, C.c_int, C.POINTER(C.c_int)], C.c_int),
@@ -147,6 +151,62 @@ class PinnedArray:
         if getattr(self, "_p", None):
             self._lib.pk_free_host(self._p)
             self._p = None
+
+
+class PinnedPool:
+    """Page-locked result buffers handed out as *leases*.
+
+    The reference returns a fresh array per call (ownership): the caller may keep it for as
+    long as it likes.  Device-to-host copies run at full PCIe rate only into page-locked memory, and
+    page-locking per call is far too slow, so results are written into buffers of this pool and the
+    caller receives a NumPy array that *owns a lease* on its buffer: the buffer goes back to the pool
+    when the last array (or view of it) referring to it is garbage-collected, never earlier.  A solver
+    that drops the previous Jacobian before asking for the next one keeps hitting the same buffer; one
+    that holds on to results simply gets further buffers (beyond ``max_bytes`` outstanding: ordinary
+    pageable arrays).  Nothing is ever overwritten behind the caller's back."""
+
+    def __init__(self, lib, max_bytes: int = 4 << 30, keep_free: int = 2):
+        self._lib, self.max_bytes, self.keep_free = lib, int(max_bytes), int(keep_free)
+        self._free: dict = {}  # doubles -> [address]
+        self.bytes = 0         # page-locked bytes owned (leased + free)
+        self.allocations = 0
+        self._closed = False
+
+    def take(self, n: int) -> np.ndarray:
+        n = int(n)
+        stack = self._free.get(n)
+        if stack:
+            addr = stack.pop()
+        else:
+            if self.bytes + 8 * n > self.max_bytes:
+                return np.empty(n, dtype=np.float64)
+            addr = self._lib.pk_alloc_host(8 * n)
+            if not addr:
+                return np.empty(n, dtype=np.float64)
+            self.bytes += 8 * n
+            self.allocations += 1
+        owner = (C.c_double * n).from_address(addr)
+        # every array derived from the one returned here keeps `owner` alive (NumPy's base chain ends
+        # at the buffer provider), so this fires exactly when the caller has let go of the result
+        weakref.finalize(owner, self._give_back, n, addr).atexit = False
+        return np.frombuffer(owner, dtype=np.float64)
+
+    def _give_back(self, n: int, addr: int):
+        stack = self._free.setdefault(n, [])
+        if self._closed or len(stack) >= self.keep_free:
+            self._lib.pk_free_host(addr)
+            self.bytes -= 8 * n
+        else:
+            stack.append(addr)
+
+    def close(self):
+        """Release the free buffers; leased ones are freed when their arrays die."""
+        self._closed = True
+        for n, stack in self._free.items():
+            for addr in stack:
+                self._lib.pk_free_host(addr)
+                self.bytes -= 8 * n
+        self._free = {}
 
 
 def cubin_cache_stats() -> tuple:
@@ -203,6 +263,9 @@ class Engine:
         self._loaded = set()
         self._pinned = {}
         self.reuse_outputs = False
+        # results of 64 KB and more come from the lease pool (see PinnedPool); POCKIT_B200_PINNED_POOL=0
+        # returns plain pageable NumPy arrays instead (slow device-to-host copies)
+        self.pool = PinnedPool(self.lib) if os.environ.get("POCKIT_B200_PINNED_POOL", "1") != "0" else None
         self._opts = ["--fmad=true"] if fastmath else []
         self._one = np.ones(self.B)
         self._zero_lam = np.zeros(self.B * max(1, lo.m))
@@ -216,6 +279,8 @@ class Engine:
         if self._h is not None:
             self.lib.pk_engine_destroy(self._h)
             self._h = None
+            if getattr(self, "pool", None) is not None:
+                self.pool.close()
 
     def __del__(self):
         try:
@@ -300,6 +365,8 @@ class Engine:
                 if mode not in self._pinned:
                     self._pinned[mode] = PinnedArray(n)
                 return self._pinned[mode].array
+            if self.pool is not None and n >= 8192:
+                return self.pool.take(n)
             return np.empty(n, dtype=np.float64)
         if out.size != n or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise ValueError("out must be a contiguous float64 array of the callback's size")
@@ -398,17 +465,45 @@ class Engine:
         self._check(self.lib.pk_eval_hessian(self._h, _ptr(x), _ptr(lam), _ptr(sig), _ptr(out)))
         return self._shape(P.HESS, out)
 
+    def _hessian_part(self, x, fct_c, fct_o, offset: int, count: int):
+        """Head / tail of the Hessian values: one evaluation of the mode, and only the requested slots
+        cross PCIe (``pk_download_range``) -- SciPy's adapter asks for ``hessian_o`` and ``hessian_c``
+        separately at every iterate (``optimizer/scipy.py:64-72``)."""
+        self.load(P.HESS)
+        if P.HESS in self.compacted or self.fin[P.HESS].get("runs") is not None:
+            if x is None:
+                raise ValueError("shaped outputs (de-duplicated pattern / mesh shard) need x")
+            full = self.hessian(x, fct_c, fct_o)  # shaped outputs: both parts live on one merged pattern / shard
+            return np.array(full) if P.HESS in self.compacted else np.array(full[..., offset : offset + count])
+        lam = np.ascontiguousarray(fct_c, dtype=np.float64)
+        if lam.size != self.B * self.lowering.m:
+            raise ValueError(f"fct_c must have {self.B * self.lowering.m} entries")
+        sig = np.ascontiguousarray(np.broadcast_to(np.asarray(fct_o, dtype=np.float64), (self.B,)))
+        if x is not None:  # None: the point already resident on the device (x-keyed cache)
+            x = self._x(x)
+            self._check(self.lib.pk_upload_x(self._h, _ptr(x)))
+        elif self.x_uploads == 0:
+            raise ValueError("x = None reuses the resident point, but none was uploaded yet")
+        self._check(self.lib.pk_upload_multipliers(self._h, _ptr(lam), _ptr(sig)))
+        self._check(self.lib.pk_run(self._h, P.HESS))
+        n = self.B * count
+        out = self.pool.take(n) if self.pool is not None and n >= 8192 else np.empty(n, dtype=np.float64)
+        self._check(self.lib.pk_download_range(self._h, P.HESS, offset, count, _ptr(out)))
+        return out if self.B == 1 else out.reshape(self.B, count)
+
     def hessian_o(self, x):
-        full = self.hessian(x, self._zero_lam[: self.B * self.lowering.m], self._one)
-        if P.HESS in self.compacted:  # de-duplicated: both parts live on the merged pattern
-            return np.array(full)
-        return np.array(full[..., : self.lowering.nnz_hess_o])
+        return self._hessian_part(x, self._zero_lam[: self.B * self.lowering.m], self._one, 0, self.lowering.nnz_hess_o)
 
     def hessian_c(self, x, fct_c):
-        full = self.hessian(x, fct_c, np.zeros(self.B))
-        if P.HESS in self.compacted:
-            return np.array(full)
-        return np.array(full[..., self.lowering.nnz_hess_o :])
+        return self._hessian_part(x, fct_c, np.zeros(self.B), self.lowering.nnz_hess_o, self.lowering.nnz_hess_c)
+
+    def out_device_pointer(self, mode: int) -> tuple:
+        """(device address, doubles) of the mode's latest result, ``[B][n_host]`` -- for device-side
+        consumers such as the NCCL gather of an instance-sharded batch (``sharding.ShardedBatch``)."""
+        self.load(mode)
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self.lib.pk_out_device_pointer(self._h, mode, C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     # ------------------------------------------------------------------ continuous error estimate
     def error_estimation_data(self, x):
@@ -486,6 +581,14 @@ class Engine:
         st = (C.c_float * (N_STAGES + 2))()
         self._check(self.lib.pk_time(self._h, mode, iters, C.byref(total), st if stages else None))
         return (total.value, list(st)) if stages else total.value
+
+    def time_stage(self, mode: int, stage: int, iters: int = 20, flush_l2: bool = True):
+        """CUDA-event times (ms) of ``iters`` single launches of one stage of ``mode`` (``plan.ST_*``; 6 =
+        per-node programs), each preceded by an untimed L2 flush."""
+        self.load(mode)
+        out = (C.c_float * iters)()
+        self._check(self.lib.pk_time_stage(self._h, mode, 1 << stage, iters, int(flush_l2), out))
+        return list(out)
 
     def time_steps(self, modes, steps: int, flush_l2: bool = True):
         """Per-step CUDA-event times (ms) of running ``modes`` back to back, inputs resident in HBM."""

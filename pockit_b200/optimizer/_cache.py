@@ -95,12 +95,22 @@ class CachedCallbacks:
         self._at(x)
         return np.array(self._call([P.HESS], fct_c, fct_o)[P.HESS], copy=True)
 
+    def _part(self, which: str, *args):
+        # the engine evaluates the Hessian mode once and copies back only the requested part
+        # (pk_download_range), at the resident point when this cache uploaded it
+        self.engine.reuse_outputs = True
+        shaped = bool(self.engine.compacted)
+        resident = self._resident and self.engine.x_uploads == self._uploads and not shaped
+        v = getattr(self.engine, which)(None if resident else self._x, *args)
+        self._resident = True
+        self._uploads = self.engine.x_uploads
+        self.stats["engine_calls"] += 1
+        return np.array(v, copy=True)
+
     def hessian_o(self, x):
         self._at(x)
-        full = self._call([P.HESS], np.zeros(self.engine.lowering.m), 1.0)[P.HESS]
-        return np.array(full if P.HESS in self.engine.compacted else full[: self.engine.lowering.nnz_hess_o], copy=True)
+        return self._part("hessian_o")
 
     def hessian_c(self, x, fct_c):
         self._at(x)
-        full = self._call([P.HESS], fct_c, 0.0)[P.HESS]
-        return np.array(full if P.HESS in self.engine.compacted else full[self.engine.lowering.nnz_hess_o :], copy=True)
+        return self._part("hessian_c", fct_c)

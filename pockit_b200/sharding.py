@@ -12,7 +12,7 @@ from typing import Callable, Optional
 
 import numpy as np
 
-__all__ = ["shard_indices", "ShardedBatch"]
+__all__ = ["shard_indices", "ShardedBatch", "device_view"]
 
 
 def shard_indices(n: int, rank: int, world: int) -> np.ndarray:
@@ -20,6 +20,23 @@ def shard_indices(n: int, rank: int, world: int) -> np.ndarray:
     if not 0 <= rank < world:
         raise ValueError("rank must be in [0, world)")
     return np.arange(rank, n, world, dtype=np.int64)
+
+
+class _DevicePointer:
+    """Minimal ``__cuda_array_interface__`` carrier: lets torch wrap an engine buffer without a copy."""
+
+    def __init__(self, address: int, shape: tuple):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(address), False), "version": 3,
+                                         "strides": None}
+
+
+def device_view(engine, mode: int):
+    """The engine's result buffer of ``mode`` as a ``[B][n]`` float64 CUDA tensor (no copy; valid until
+    the mode is evaluated again or the engine is closed)."""
+    import torch
+
+    address, count = engine.out_device_pointer(mode)
+    return torch.as_tensor(_DevicePointer(address, (engine.B, count // engine.B)), device=torch.device("cuda", engine.device))
 
 
 class ShardedBatch:
@@ -85,3 +102,25 @@ class ShardedBatch:
             ids = shard_indices(self.n, r, self.world)
             out[ids] = t[: len(ids)].cpu().numpy()
         return out
+
+    def gather_device(self, mode: int):
+        """NCCL all-gather of the local engine's latest ``mode`` values, device to device over NVLink:
+        every rank receives the global ``[n][width]`` CUDA tensor in instance order.  The local shard is
+        read straight from the engine's output buffer (``pk_out_device_pointer``): no host round trip."""
+        import torch
+        import torch.distributed as dist
+
+        local = device_view(self.local.engine, mode)
+        if self.world == 1:
+            return local
+        width = local.shape[1]
+        per = (self.n + self.world - 1) // self.world
+        if len(self.idx) == per:
+            send = local
+        else:  # the last ranks own one instance less: pad
+            send = torch.zeros((per, width), dtype=torch.float64, device=local.device)
+            send[: len(self.idx)] = local
+        recv = torch.empty((self.world, per, width), dtype=torch.float64, device=local.device)
+        dist.all_gather_into_tensor(recv.view(-1), send.contiguous().view(-1))
+        # rank r holds instances r, r + world, ...: global instance b sits at recv[b % world, b // world]
+        return recv.transpose(0, 1).reshape(per * self.world, width)[: self.n]

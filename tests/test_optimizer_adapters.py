@@ -37,6 +37,19 @@ class EmuEngine:
         return res
 
 
+    def hessian_o(self, x):
+        self.calls.append((x is not None, ("hessian_o",)))
+        if x is not None:
+            self.upload(x)
+        return self.e.run(P.HESS, self.x, np.zeros(self.lowering.m), 1.0)[: self.lowering.nnz_hess_o]
+
+    def hessian_c(self, x, fct_c):
+        self.calls.append((x is not None, ("hessian_c",)))
+        if x is not None:
+            self.upload(x)
+        return self.e.run(P.HESS, self.x, fct_c, 0.0)[self.lowering.nnz_hess_o:]
+
+
 class FakeSystem:
     def __init__(self, S):
         self._S = S
