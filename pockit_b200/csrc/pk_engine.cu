@@ -650,6 +650,9 @@ static PkCtx make_ctx(pk_engine* e, const ModeState& ms) {
   cx.X = e->X; cx.LAM = e->LAM; cx.SIG = e->SIG; cx.S = ms.S; cx.W = ms.W; cx.OUT = ms.OUT;
   cx.dpool = e->dpool; cx.ipool = e->ipool;
   cx.L = e->dims.L; cx.m = e->dims.m; cx.n_scalar = ms.n_scalar; cx.n_out = ms.n_out;
+  // streaming result stores unless the compaction pass re-reads the values (POCKIT_B200_STREAM=0: plain stores)
+  static const bool stream_env = !(getenv("POCKIT_B200_STREAM") && getenv("POCKIT_B200_STREAM")[0] == '0');
+  cx.stream = (stream_env && !ms.n_compact) ? 1 : 0;
   return cx;
 }
 
@@ -1163,19 +1166,21 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
     CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     CK(cudaEventRecord(e->fork, e->stream));
     int rc = 0;
-    // Schedule of a set.  Every kernel of it either fills the machine on its own (the HBM-bound block
-    // expansions; on wide models also the per-node programs) or is a short link of a latency-bound
-    // chain, so what is released together merely shares the SMs and everything finishes late.  The
-    // critical path is  node program -> expansion  of the modes that have one (Jacobian, Hessian) with
-    // the expansions chained; it gets the machine first:
+    // Schedule of a set.  Opt-in alternative (POCKIT_B200_STAGGER=1|2): the critical path -- node
+    // program -> expansion of the modes that have one (Jacobian, Hessian), expansions chained -- gets
+    // the machine first:
     //   1. the per-node program of the first expansion mode runs alone, its expansion starts right behind;
     //   2. the next expansion mode's per-node program is released when the previous one has finished
     //      (it overlaps the running, HBM-bound expansion) -- its expansion follows the chain;
     //   3. the small callbacks (objective, gradient, constraints) are released behind the last of those
     //      per-node programs (POCKIT_B200_STAGGER=1: behind the first) and hide under the expansions.
-    // POCKIT_B200_STAGGER=0: everything is released at once (the round-1 schedule, largest first).
+    // POCKIT_B200_STAGGER=0 (default): everything is released at once, largest first.
+    // Measured on B200 (round 2, profiles/r02_call3_stagger_ab.log) the staggered schedules are SLOWER
+    // -- robot_arm 60.1 -> 59.0 (=1) / 64.3 us (=2), humanoid 143.1 -> 145.6 / 156.6, rocket 59.9 -> 67.9 /
+    // 73.3 -- the kernels released together do overlap usefully; holding the small callbacks back
+    // only moves them to the tail.  Kept as an opt-in switch.
     const char* sg = getenv("POCKIT_B200_STAGGER");
-    const int stagger = sg ? atoi(sg) : 2;
+    const int stagger = sg ? atoi(sg) : 0;
     std::vector<int> order;
     if (stagger > 0) {
       std::vector<int> big, small;

@@ -25,6 +25,52 @@ struct Geo {
 __device__ __forceinline__ long long list_base(const Geo& g, int l) { return (long long)l * g.list_stride + (g.mis ? 1 + (l & 3) : 0); }
 
 // ---- baseline: the parameter-driven column walk (pk_expand_cols)
+template <int ST>
+__device__ __forceinline__ void store(double* p, double v) {
+  if (ST == 1) __stcs(p, v);        // streaming (evict-first) store
+  else if (ST == 2) __stwt(p, v);   // write-through
+  else if (ST == 3) __stcg(p, v);   // cache at L2 only
+  else *p = v;
+}
+
+// variants of the column walk: block size, unroll depth, store cache operator
+template <bool LAMF, int THREADS, int UNROLL, int ST>
+__global__ void __launch_bounds__(THREADS) cols_v(double* __restrict__ out_all, const double* __restrict__ W, const double* __restrict__ LAM,
+                                                  const double* __restrict__ unit, const double* __restrict__ width, Geo g) {
+  extern __shared__ double sm[];
+  const int n = g.n, rows = g.rows, bn = n * rows;
+  double* u_s = sm;
+  double* lam_s = sm + bn;
+  const unsigned pairs = g.nK * n;
+  const unsigned t0 = blockIdx.x * THREADS;
+  if (t0 >= pairs) return;
+  const unsigned t = t0 + threadIdx.x;
+  const bool live = t < pairs;
+  const unsigned tt = live ? t : pairs - 1;
+  const unsigned K = tt / n, cc = tt - K * n, K0 = t0 / n;
+  const int l = blockIdx.y;
+  const double sv = W[(size_t)l * g.Lm + 1 + (size_t)K * g.step + cc];
+  const double w = width[K];
+  for (int q = threadIdx.x; q < bn; q += THREADS) u_s[q] = -1.0 * unit[q];
+  if (LAMF) {
+    unsigned tl = t0 + THREADS - 1;
+    if (tl >= pairs) tl = pairs - 1;
+    const int n_lam = (int)(tl / n - K0 + 1) * rows;
+    for (int q = threadIdx.x; q < n_lam; q += THREADS) lam_s[q] = LAM[(size_t)K0 * rows + q];
+  }
+  __syncthreads();
+  if (!live) return;
+  double* __restrict__ out = out_all + list_base(g, l) + (size_t)K * bn + cc;
+  const double* u = u_s + cc;
+  const double* lm = lam_s + (K - K0) * rows;
+#pragma unroll UNROLL
+  for (int r = 0; r < rows; ++r) {
+    double v = (u[r * n] * w) / 2.0;
+    if (LAMF) v = v * lm[r];
+    store<ST>(out + r * n, v * sv);
+  }
+}
+
 template <bool LAMF>
 __global__ void __launch_bounds__(128) cols(double* __restrict__ out_all, const double* __restrict__ W, const double* __restrict__ LAM,
                                             const double* __restrict__ unit, const double* __restrict__ width, Geo g) {
@@ -273,6 +319,28 @@ static void study(const char* name, int n, int rows, int step, unsigned nK, int 
       cudaDeviceSynchronize();
       cudaMemcpy(ref.data(), buf[0], 8 * slots, cudaMemcpyDeviceToHost);
       report("cols (pk_expand_cols)", us, false);
+#define COLSV(T, U, ST, label)                                                                 \
+  {                                                                                            \
+    const size_t vsm = 8 * (size_t)(bn + (T / n + 2) * rows);                                  \
+    auto lf = [&](int w) {                                                                     \
+      dim3 grid((pairs + T - 1) / T, lists);                                                   \
+      if (lamf) cols_v<true, T, U, ST><<<grid, T, vsm>>>(buf[w], W, LAM, unit, width, g);      \
+      else cols_v<false, T, U, ST><<<grid, T, vsm>>>(buf[w], W, LAM, unit, width, g);          \
+    };                                                                                         \
+    cudaMemset(buf[0], 0, 8 * slots);                                                          \
+    us = timeit(lf, iters);                                                                    \
+    report(label, us, true);                                                                   \
+  }
+      COLSV(64, 4, 0, "cols 64 threads");
+      COLSV(256, 4, 0, "cols 256 threads");
+      COLSV(128, 2, 0, "cols unroll 2");
+      COLSV(128, 10, 0, "cols unroll 10");
+      COLSV(128, 20, 0, "cols unroll 20");
+      COLSV(128, 4, 1, "cols st.cs");
+      COLSV(128, 4, 2, "cols st.wt");
+      COLSV(128, 4, 3, "cols st.cg");
+      COLSV(64, 10, 1, "cols 64 threads unroll 10 st.cs");
+      if (getenv("MB_COLS_ONLY")) continue;
 #define FLAT(SMV, GPT, label)                                                                  \
   {                                                                                            \
     auto lf = [&](int w) {                                                                     \

@@ -14,7 +14,13 @@ for name in sys.argv[1:] or ["humanoid"]:
     builder, scheme, kw, B = CONFIGS[name]
     S = problems.BUILDERS[builder](importlib.import_module(f"pockit_b200.{scheme}"), **kw)
     x, lam, sigma = problems.evaluation_point(S)
-    eng = Engine(S.lowering); eng.upload(x, lam, sigma)
+    if B > 1:  # batched configuration: B instances around the evaluation point
+        import numpy as np
+        rng = np.random.default_rng(0)
+        x = x[None, :] + 1e-2 * rng.normal(size=(B, len(x)))
+        lam = np.tile(lam, (B, 1))
+        sigma = np.full(B, sigma)
+    eng = Engine(S.lowering, batch=B, fastmath=S._fastmath); eng.upload(x, lam, sigma)
     for m in eng._mode_ids:
         eng.time(m, iters=5)
         tot, st = eng.time(m, iters=20, stages=True)
