@@ -298,6 +298,25 @@ def expansion_roofline(eng, lo, P, peak, iters=20):
             "algorithmic_bytes_per_launch": alg, "launch_ms": k_ms, "launches_timed": iters}
 
 
+def platform_d2h_GBps(torch, nbytes_per_rank: int, maxed, barrier, reps: int = 5) -> float:
+    """What the box gives: every rank copies ``nbytes_per_rank`` from its GPU into its own page-locked host
+    buffer at the same time (plain cudaMemcpyAsync, CUDA events, max over ranks).  Returns GB/s PER RANK;
+    the end-to-end path is bound by world x this figure (the device-to-host link(s) and host memory)."""
+    n = max(1, nbytes_per_rank // 8)
+    dev = torch.empty(n, dtype=torch.float64, device="cuda").fill_(1.0)
+    host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    host.copy_(dev)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        host.copy_(dev, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    t = maxed(a.elapsed_time(b) / 1e3) / reps
+    return 8 * n / t / 1e9
+
+
 def short_config(name, S, x, lam, sigma, P, peak, steps, batch=1, fixed=None):
     """One of the other BASELINE configurations in short form: device-resident set time (flushed), e2e
     through the host API, roofline fractions."""
@@ -611,6 +630,7 @@ def bench_single(args, S, eng, x, lam, sigma, P, peak, peak_source, clk, value, 
     e2e_page_t = (time.perf_counter() - t0) / n_page
     eng.pool = pool
 
+    link = platform_d2h_GBps(torch, d2h, lambda v: v, torch.cuda.synchronize)
     compact = None
     if not args.no_compact:  # opt-in de-duplicated patterns (outside the reference's pattern contract)
         S.compact_patterns = True
@@ -656,6 +676,7 @@ def bench_single(args, S, eng, x, lam, sigma, P, peak, peak_source, clk, value, 
         },
         "e2e": {"value": args.steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1000.0 * e2e_t / args.steps,
+                "platform_d2h_GBps": link, "frac_of_platform_d2h": (d2h / (e2e_t / args.steps) / 1e9) / link,
                 "api": "System.evaluate(x, lam, sigma) -> pk_eval_set: one upload, per-mode streams, copies overlapped",
                 "outputs": "arrays owned by the caller (leases on the engine's page-locked pool; nothing is overwritten while referenced)",
                 "caller_keeps_previous_results": {"value": 1.0 / e2e_hold_t, "ms_per_step": 1000.0 * e2e_hold_t},
@@ -707,6 +728,13 @@ def bench_sharded(args, S, eng, x, lam, sigma, P, peak, peak_source, clk, value,
     L, m, nj, nh, h2d, d2h = dims
     lo = S.lowering
     eng.close()
+
+    def maxed(v):
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    link = platform_d2h_GBps(torch, d2h // world, maxed, barrier)  # all ranks copy their share concurrently
     # ---- end to end: rank 0 is the caller (host buffers in / out), the other ranks serve their shares
     ms = MeshShardedSystem(S, rank=rank, world=world, device=local)
     ms.pinned_outputs = True  # results are views of the shared page-locked mapping all ranks copy into
@@ -748,6 +776,8 @@ def bench_sharded(args, S, eng, x, lam, sigma, P, peak, peak_source, clk, value,
                              "frac_of_all_gpus": set_bytes / (t_max / args.steps) / 1e9 / (peak * world)},
             "e2e": {"value": args.steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000.0 * e2e_t / args.steps, "ms_per_callback": each,
+                    "platform_d2h_GBps_aggregate": link * world, "platform_d2h_GBps_per_rank": link,
+                    "frac_of_platform_d2h": (d2h / (e2e_t / args.steps) / 1e9) / (link * world),
                     "api": "MeshShardedSystem.evaluate(x, lam, sigma) on rank 0: x published in a shared page-locked mapping, every rank "
                            "copies its share of the Jacobian / Hessian values back over its own PCIe link",
                     "bit_identical_to_unsharded": bool(exact), "collective_in_data_path": "none"},

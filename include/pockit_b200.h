@@ -38,10 +38,11 @@ enum {
   PK_MODE_JACOBIAN = 3,    /* SystemBase.jacobian    systembase.py:676 */
   PK_MODE_HESSIAN = 4,     /* SystemBase.hessian     systembase.py:820 (hessian_o :735, hessian_c :786) */
   PK_N_CALLBACKS = 5,
-  /* all five callbacks at one (x, lambda, sigma) as ONE pipeline: a single per-node program evaluates
+  /* several callbacks at one (x, lambda, sigma) as ONE pipeline: a single per-node program evaluates
    * every leaf once, one reduction and one system program feed all consumers; outputs in one buffer
-   * [objective | gradient | constraints | Jacobian values | Hessian values].  Used by pk_run_set /
-   * pk_eval_set / pk_time_steps when all five callbacks are requested and this mode is loaded. */
+   * [objective | gradient | constraints | Jacobian values | Hessian values] (the covered ones:
+   * pk_mode_desc.sub_count > 0 -- all five, or the three small callbacks).  Used by pk_run_set /
+   * pk_time_steps when every covered callback is requested and this mode is loaded. */
   PK_MODE_SET = 5,
   PK_N_MODES = 6
 };
@@ -199,9 +200,9 @@ int pk_download(pk_engine *e, int mode, double *out);
  * (systembase.py:735, 786) are the head / tail of the Hessian values -- one evaluation, only the
  * requested part crosses PCIe */
 int pk_download_range(pk_engine *e, int mode, int64_t offset, int64_t count, double *out);
-/* device address ([B][n_out] doubles) and total count of a mode's result, for device-side consumers
- * (e.g. an NCCL all-gather of instance-sharded batches) */
-int pk_out_device_pointer(pk_engine *e, int mode, void **ptr, int64_t *count);
+/* device address of a mode's latest result for device-side consumers (e.g. an NCCL all-gather of
+ * instance-sharded batches): *count values per instance, instances *stride doubles apart */
+int pk_out_device_pointer(pk_engine *e, int mode, void **ptr, int64_t *count, int64_t *stride);
 /* time `iters` back-to-back runs with CUDA events on the engine stream; ms_total covers the
  * whole mode, ms_stage[s] the kernels of each stage (s = 0..PK_N_STAGES-1 jobs, PK_N_STAGES = node
  * programs, PK_N_STAGES+1 = system program), measured in separate passes. */

@@ -656,7 +656,7 @@ static PkCtx make_ctx(pk_engine* e, const ModeState& ms) {
   return cx;
 }
 
-static bool use_pipeline(pk_engine* e, const int* modes, int n_modes);
+static unsigned use_pipeline(pk_engine* e, const int* modes, int n_modes);
 
 static inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
 
@@ -687,10 +687,12 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
   ModeState& ms = e->mode[mode];
   if (!ms.loaded) return fail("mode not loaded");
   const int B = e->dims.batch;
-  if (mode == PK_MODE_SET)
-    for (int k = 0; k < PK_N_CALLBACKS; ++k) e->mode[k].in_set = true;
-  else
+  if (mode == PK_MODE_SET) {
+    for (int k = 0; k < PK_N_CALLBACKS; ++k)
+      if (ms.sub_cnt[k] > 0) e->mode[k].in_set = true;  // the callbacks this pipeline covers
+  } else {
     ms.in_set = false;
+  }
   PkCtx cx = make_ctx(e, ms);
   auto on = [&](int stage) { return (stage_mask & (1u << stage)) != 0; };
   if (on(PK_N_STAGES)) {
@@ -937,15 +939,24 @@ extern "C" int pk_download_range(pk_engine* e, int mode, int64_t offset, int64_t
   return 0;
 }
 
-// Device address of a mode's result buffer ([B][n_out] doubles, or the compacted values): lets a
+// Device address of a mode's latest result: `count` values per instance, instances `stride` doubles
+// apart (stride > count when the values are a slice of the set pipeline's combined output).  Lets a
 // caller hand the values to a collective (NCCL all-gather of sharded batches) without a host round trip.
-extern "C" int pk_out_device_pointer(pk_engine* e, int mode, void** ptr, int64_t* count) {
+extern "C" int pk_out_device_pointer(pk_engine* e, int mode, void** ptr, int64_t* count, int64_t* stride) {
   if (!e || !ptr || mode < 0 || mode >= PK_N_MODES) return fail("pk_out_device_pointer: bad argument");
   ModeState& ms = e->mode[mode];
   if (!ms.loaded) return fail("pk_out_device_pointer: mode not loaded");
-  if (ms.in_set) return fail("pk_out_device_pointer: the latest values live in the set pipeline's combined output");
+  if (mode < PK_N_CALLBACKS && ms.in_set) {  // a slice of the set pipeline's combined output
+    const ModeState& set = e->mode[PK_MODE_SET];
+    *ptr = (void*)(set.OUT + set.sub_off[mode]);
+    if (count) *count = set.sub_cnt[mode];
+    if (stride) *stride = set.n_out;
+    return 0;
+  }
   *ptr = ms.n_compact ? (void*)ms.OUTC : (void*)ms.OUT;
-  if (count) *count = (ms.n_compact ? ms.n_compact : ms.n_out) * (int64_t)e->dims.batch;
+  const int64_t n = ms.n_compact ? ms.n_compact : ms.n_out;
+  if (count) *count = n;
+  if (stride) *stride = n;
   return 0;
 }
 
@@ -1046,8 +1057,10 @@ extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, con
   if (hess && (!lam || !sig)) return fail("pk_eval_set: multipliers required for the Hessian");
   if (x && pk_upload_x(e, x)) return 1;
   if (hess && pk_upload_multipliers(e, lam, sig)) return 1;
-  if (use_pipeline(e, modes, n_modes)) {
-    // one pipeline for all five; the copies of its slices follow on the same stream, largest first
+  unsigned asked = 0;
+  for (int k = 0; k < n_modes; ++k) asked |= 1u << modes[k];
+  if (use_pipeline(e, modes, n_modes) == asked) {
+    // one pipeline for everything that was asked for; the copies of its slices follow on the same stream, largest first
     CK(cudaEventRecord(e->fork, e->stream));
     ModeState& ps = e->mode[PK_MODE_SET];
     CK(cudaStreamWaitEvent(ps.stream, e->fork, 0));
@@ -1134,26 +1147,34 @@ extern "C" int pk_time_stage(pk_engine* e, int mode, unsigned stage_mask, int it
 // Launch several callbacks at the same x as ONE graph: every mode runs on its own stream (its
 // tables and output buffer are private), forked from and joined to the engine stream, so the
 // latency-bound small callbacks overlap the HBM-bound expansions and the host pays one launch.
-// All five callbacks requested, the set pipeline loaded, and no per-callback output shaping
-// (de-duplicated pattern / mesh shard) in the way: evaluate them as PK_MODE_SET.
-static bool use_pipeline(pk_engine* e, const int* modes, int n_modes) {
-  if (n_modes != PK_N_CALLBACKS || !e->mode[PK_MODE_SET].loaded) return false;
+// The callbacks the loaded set pipeline covers (all five, or the three small ones) are evaluated as
+// PK_MODE_SET when all of them are requested and no per-callback output shaping (de-duplicated
+// pattern / mesh shard) is in the way; use_pipeline returns their bit mask (0: no pipeline).
+static unsigned use_pipeline(pk_engine* e, const int* modes, int n_modes) {
+  const ModeState& set = e->mode[PK_MODE_SET];
+  if (!set.loaded) return 0;
   const char* env = getenv("POCKIT_B200_SET");
-  if (env && env[0] == '0') return false;  // (the Python layer only loads the pipeline when asked to)
-  unsigned seen = 0;
+  if (env && env[0] == '0') return 0;
+  unsigned covered = 0, seen = 0;
+  for (int k = 0; k < PK_N_CALLBACKS; ++k)
+    if (set.sub_cnt[k] > 0) covered |= 1u << k;
   for (int k = 0; k < n_modes; ++k) {
-    if (modes[k] < 0 || modes[k] >= PK_N_CALLBACKS) return false;
-    const ModeState& ms = e->mode[modes[k]];
-    if (ms.n_compact || !ms.dl_runs.empty()) return false;
+    if (modes[k] < 0 || modes[k] >= PK_N_CALLBACKS) return 0;
     seen |= 1u << modes[k];
   }
-  return seen == (1u << PK_N_CALLBACKS) - 1;
+  if (!covered || (seen & covered) != covered) return 0;  // every covered callback must be asked for
+  for (int k = 0; k < PK_N_CALLBACKS; ++k)
+    if ((covered >> k & 1u) && (e->mode[k].n_compact || !e->mode[k].dl_runs.empty())) return 0;
+  return covered;
 }
 
 static int run_set(pk_engine* e, const int* modes, int n_modes) {
-  std::vector<int> want(modes, modes + n_modes);
-  const bool pipeline = use_pipeline(e, modes, n_modes);
-  if (pipeline) want.assign(1, PK_MODE_SET);
+  std::vector<int> want;
+  const unsigned covered = use_pipeline(e, modes, n_modes);
+  const bool pipeline = covered != 0;
+  for (int k = 0; k < n_modes; ++k)
+    if (!(covered >> modes[k] & 1u)) want.push_back(modes[k]);
+  if (pipeline) want.push_back(PK_MODE_SET);
   n_modes = (int)want.size();
   modes = want.data();
   if (!e->set_graph || want != e->set_modes) {
@@ -1260,10 +1281,10 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
   CK(cudaGraphLaunch(e->set_graph, e->stream));
   e->launches += e->set_launches;
   // replays do not pass through launch_mode: keep track of where the latest values live
-  if (pipeline)
-    for (int k = 0; k < PK_N_CALLBACKS; ++k) e->mode[k].in_set = true;
-  else
-    for (int k = 0; k < n_modes; ++k) e->mode[want[k]].in_set = false;
+  for (int k = 0; k < n_modes; ++k)
+    if (want[k] < PK_N_CALLBACKS) e->mode[want[k]].in_set = false;
+  for (int k = 0; k < PK_N_CALLBACKS; ++k)
+    if (covered >> k & 1u) e->mode[k].in_set = true;
   return 0;
 }
 

@@ -109,7 +109,7 @@ def load_library():
         "pk_sync": ([vp], C.c_int),
         "pk_download": ([vp, C.c_int, vp], C.c_int),
         "pk_download_range": ([vp, C.c_int, C.c_int64, C.c_int64, vp], C.c_int),
-        "pk_out_device_pointer": ([vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)], C.c_int),
+        "pk_out_device_pointer": ([vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         "pk_time": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
         "pk_time_stage": ([vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "pk_time_steps": ([vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
@@ -226,16 +226,23 @@ class Engine:
         self.lowering = lowering
         self.B = int(batch)
         self.shard = shard
+        # The set pipeline (plan.SET): callbacks evaluated as ONE pipeline -- one per-node program with a
+        # shared CSE, one reduction, one system program -- when a whole set is run (pk_run_set).
+        #   POCKIT_B200_SET=small (default)  the three latency-bound callbacks (objective, gradient,
+        #       constraints): one chain of small kernels instead of three beside the two expansions;
+        #   POCKIT_B200_SET=1  all five (measured on B200 in round 1: SLOWER than separate pipelines,
+        #       robot_arm 76 vs 67 us per set -- its single chain queues behind the block expansions);
+        #   POCKIT_B200_SET=0  none.
+        # Needs a whole plan (no mesh shard / fused walk).
+        choice = os.environ.get("POCKIT_B200_SET", "small")
+        subs = {"0": (), "1": P.SET_ORDER}.get(choice, P.SMALL_SET)
+        self.has_set = shard is None and os.environ.get("POCKIT_B200_FUSED", "0") != "1" and bool(subs)
+        self.set_subs = tuple(subs) if self.has_set else ()
         self.plan = P.DevicePlan(lowering, self.B, fastmath, shard=shard,
                                  fused=shard is None and os.environ.get("POCKIT_B200_FUSED", "0") == "1",
-                                 node_groups=int(os.environ.get("POCKIT_B200_NODE_GROUPS", "1")))
+                                 node_groups=int(os.environ.get("POCKIT_B200_NODE_GROUPS", "1")),
+                                 set_subs=subs or P.SET_ORDER)
         self.fin = {}
-        # The fused set pipeline (plan.SET: one per-node program, one reduction, one system program for
-        # all five callbacks) is opt-in, POCKIT_B200_SET=1: measured on B200 (round 1, tools/probe3.py) it
-        # is SLOWER than five concurrent per-callback pipelines -- robot_arm LGR 2000x20 76 vs 67 us per set,
-        # humanoid 100 k nodes 154 vs 145 us -- because its single chain of small kernels queues behind the
-        # block expansions instead of overlapping them.  Needs a whole plan (no mesh shard / fused walk).
-        self.has_set = shard is None and not self.plan.fused and os.environ.get("POCKIT_B200_SET", "0") == "1"
         self._mode_ids = list(range(N_CALLBACKS)) + ([P.SET] if self.has_set else [])
         for m in self._mode_ids:
             self.plan.mode(m)
@@ -324,7 +331,7 @@ class Engine:
         d.grad_offset, d.grad_count = (int(v) for v in f["grad_range"])
         if mode == P.SET:
             for k in range(N_CALLBACKS):
-                d.sub_offset[k], d.sub_count[k] = (int(v) for v in f["sub_range"][k])
+                d.sub_offset[k], d.sub_count[k] = (int(v) for v in f["sub_range"].get(k, (0, 0)))
         keep = []
         for s in range(N_STAGES):
             arr = np.ascontiguousarray(f["jobs"][s])
@@ -346,7 +353,7 @@ class Engine:
         which the engine then runs instead of five separate pipelines."""
         for m in modes:
             self.load(m)
-        if self.has_set and sorted(modes) == list(range(N_CALLBACKS)) and not self.compacted:
+        if self.has_set and set(self.set_subs) <= set(modes) and not (self.compacted & set(self.set_subs)):
             self.load(P.SET)
 
     # ------------------------------------------------------------------ host-to-host callbacks
@@ -498,12 +505,14 @@ class Engine:
         return self._hessian_part(x, fct_c, np.zeros(self.B), self.lowering.nnz_hess_o, self.lowering.nnz_hess_c)
 
     def out_device_pointer(self, mode: int) -> tuple:
-        """(device address, doubles) of the mode's latest result, ``[B][n_host]`` -- for device-side
-        consumers such as the NCCL gather of an instance-sharded batch (``sharding.ShardedBatch``)."""
+        """(device address, values per instance, doubles between instances) of the mode's latest result --
+        for device-side consumers such as the NCCL gather of an instance-sharded batch
+        (``sharding.ShardedBatch``).  The stride exceeds the count when the values are a slice of the
+        set pipeline's combined output."""
         self.load(mode)
-        p, n = C.c_void_p(), C.c_int64()
-        self._check(self.lib.pk_out_device_pointer(self._h, mode, C.byref(p), C.byref(n)))
-        return p.value, n.value
+        p, n, stride = C.c_void_p(), C.c_int64(), C.c_int64()
+        self._check(self.lib.pk_out_device_pointer(self._h, mode, C.byref(p), C.byref(n), C.byref(stride)))
+        return p.value, n.value, stride.value
 
     # ------------------------------------------------------------------ continuous error estimate
     def error_estimation_data(self, x):

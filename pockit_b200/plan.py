@@ -39,6 +39,11 @@ OBJ, CONS, GRAD, JAC, HESS, SET = range(6)
 # one system program feed all consumers, and the outputs land in one buffer laid out
 # [objective | gradient | constraints | Jacobian values | Hessian values] (SET_ORDER).
 SET_ORDER = (OBJ, GRAD, CONS, JAC, HESS)
+# The pipeline may also cover a subset (DevicePlan(set_subs=...)); the engine's default is the three
+# latency-bound callbacks SMALL_SET, whose separate chains of 3-5 small kernels each become ONE chain
+# (one per-node program with a shared CSE, one reduction, one system program, defects, gradient
+# gather) while the Jacobian and the Hessian keep their own pipelines beside it.
+SMALL_SET = (OBJ, GRAD, CONS)
 ST_REDUCE, ST_DEFECT, ST_GENERIC, ST_EXPAND, ST_GRAD_RANGE, ST_GRAD_SCALAR = range(6)
 J_CONST, J_KRON, J_EXPAND_TABLE, J_SCALED, J_SYS, J_OUTER, J_TRIL = range(7)
 F_A_SCALAR, F_B_SCALAR, F_A_UNIT, F_B_UNIT, F_LAM = 1, 2, 4, 8, 16
@@ -347,7 +352,7 @@ class ModePlan:
             if self.owner.shard is not None or self.owner.fused:
                 raise ValueError("the set pipeline is not planned for mesh shards / the fused variant")
             off = 0
-            for sub in SET_ORDER:
+            for sub in self.owner.set_subs:
                 self.sub, self.base = sub, off
                 count = self._build_one(sub)
                 self.sub_range[sub] = (off, count)
@@ -608,8 +613,12 @@ class DevicePlan:
     """Pools + per-mode plans for one lowered system."""
 
     def __init__(self, lo: SystemLowering, batch: int = 1, fastmath: bool = False, fused: bool = False,
-                 shard: Optional[tuple] = None, node_groups: int = 1):
+                 shard: Optional[tuple] = None, node_groups: int = 1, set_subs: tuple = SET_ORDER):
         self.lo = lo
+        # callbacks the set pipeline (mode SET) covers, in SET_ORDER
+        self.set_subs = tuple(m for m in SET_ORDER if m in set(set_subs))
+        if not self.set_subs:
+            raise ValueError("set_subs must name at least one callback")
         self.B = int(batch)
         self.fastmath = fastmath
         if shard is not None:

@@ -25,9 +25,9 @@ def shard_indices(n: int, rank: int, world: int) -> np.ndarray:
 class _DevicePointer:
     """Minimal ``__cuda_array_interface__`` carrier: lets torch wrap an engine buffer without a copy."""
 
-    def __init__(self, address: int, shape: tuple):
+    def __init__(self, address: int, shape: tuple, strides=None):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(address), False), "version": 3,
-                                         "strides": None}
+                                         "strides": strides}
 
 
 def device_view(engine, mode: int):
@@ -35,8 +35,9 @@ def device_view(engine, mode: int):
     the mode is evaluated again or the engine is closed)."""
     import torch
 
-    address, count = engine.out_device_pointer(mode)
-    return torch.as_tensor(_DevicePointer(address, (engine.B, count // engine.B)), device=torch.device("cuda", engine.device))
+    address, count, stride = engine.out_device_pointer(mode)
+    strides = None if stride == count else (8 * stride, 8)
+    return torch.as_tensor(_DevicePointer(address, (engine.B, count), strides), device=torch.device("cuda", engine.device))
 
 
 class ShardedBatch:

@@ -67,9 +67,9 @@ def _ptr(a):
 
 
 class HostEmu:
-    def __init__(self, system, batch=1, fixed=None, fused=False, shard=None, node_groups=1):
+    def __init__(self, system, batch=1, fixed=None, fused=False, shard=None, node_groups=1, set_subs=P.SET_ORDER):
         self.lo = system.lowering
-        self.dp = P.DevicePlan(self.lo, batch, fused=fused, shard=shard, node_groups=node_groups)
+        self.dp = P.DevicePlan(self.lo, batch, fused=fused, shard=shard, node_groups=node_groups, set_subs=set_subs)
         self.B = batch
         modes = range(6) if shard is None and not fused else range(5)  # + the fused set pipeline
         for m in modes:

@@ -129,12 +129,13 @@ def test_size_independent_properties_at_full_size():
     np.testing.assert_allclose(g @ d, fdo, rtol=1e-6, atol=1e-8)
 
 
-@pytest.mark.parametrize("pipeline", ["0", "1"])
+@pytest.mark.parametrize("pipeline", ["0", "1", "small"])
 def test_evaluation_set_graph_matches_single_callbacks(pipeline, monkeypatch):
     """pk_run_set (all callbacks at one x as one graph) against the five separate host-to-host
-    callbacks.  Default (POCKIT_B200_SET=0): one stream per callback, the same kernels ->
-    bit-identical.  POCKIT_B200_SET=1: the fused set pipeline (one per-node program for all five; its
-    single CSE may regroup a product) -> within the parity tolerance."""
+    callbacks.  POCKIT_B200_SET=0: one stream per callback, the same kernels -> bit-identical.
+    POCKIT_B200_SET=small (the default): objective / gradient / constraints as one pipeline (its single
+    CSE may regroup a product -> within the parity tolerance), Jacobian / Hessian bit-identical.
+    POCKIT_B200_SET=1: one pipeline for all five."""
     import pockit_b200.lobatto as lob
     from pockit_b200 import plan as P
     from pockit_b200 import problems
@@ -147,7 +148,8 @@ def test_evaluation_set_graph_matches_single_callbacks(pipeline, monkeypatch):
         P.JAC: S.jacobian(x), P.HESS: S.hessian(x, lam, sigma),
     }
     eng = S.engine
-    assert eng.has_set == (pipeline == "1")
+    assert eng.has_set == (pipeline != "0")
+    covered = {"0": (), "1": P.SET_ORDER, "small": P.SMALL_SET}[pipeline]  # "small" is the engine's default
     modes = [P.OBJ, P.GRAD, P.CONS, P.JAC, P.HESS]
     eng.upload(x, lam, sigma)
     for _ in range(3):  # replays of the captured graph
@@ -155,7 +157,7 @@ def test_evaluation_set_graph_matches_single_callbacks(pipeline, monkeypatch):
     eng.sync()
     for m in modes:
         got = np.atleast_1d(eng.download(m))
-        if pipeline == "0":
+        if m not in covered:
             assert np.array_equal(got, single[m]), P.MODES[m]
         else:
             assert_close(got, single[m], P.MODES[m])

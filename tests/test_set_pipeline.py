@@ -52,3 +52,22 @@ def test_set_pipeline_batched():
         off, cnt = sub[m]
         assert_close(out[:, off : off + cnt], E.run(m, *args), P.MODES[m])
     assert_close(out[:, 0], E.run(P.OBJ, X).reshape(-1), "objective")
+
+
+@pytest.mark.parametrize("case", ["general_lgl", "general_lgr", "rocket_lgl_4x5", "robot_arm_lgr_6x20", "quadrotor_lgl_14x6",
+                                  "humanoid_lgl_4x5", "lqr_lgl_10x10", "static_only_lgl", "tiny_lgl_1x3"])
+def test_small_set_pipeline_covers_the_three_small_callbacks(case):
+    """The engine's default: the pipeline covers objective, gradient and constraints only (plan.SMALL_SET);
+    the Jacobian and the Hessian keep their own plans."""
+    S, g = build(case), load(case)
+    E = HostEmu(S, set_subs=P.SMALL_SET)
+    x = g["x"]
+    out = E.run(P.SET, x)
+    sub = E.fin[P.SET]["sub_range"]
+    assert sorted(sub) == sorted(P.SMALL_SET) and sum(c for _, c in sub.values()) == len(out)
+    assert sub[P.OBJ] == (0, 1) and sub[P.GRAD] == (1, S.L) and sub[P.CONS] == (1 + S.L, len(S.c_lb))
+    assert_close(out[0], g["objective"], "objective")
+    assert_close(out[1 : 1 + S.L], g["gradient"], "gradient")
+    assert_close(out[1 + S.L :], g["constraints"], "constraints")
+    # no Jacobian / Hessian leaves in the shared program
+    assert len(E.fin[P.SET]["source"]) < len(E.fin[P.HESS]["source"]) + len(E.fin[P.GRAD]["source"]) + len(E.fin[P.CONS]["source"])
