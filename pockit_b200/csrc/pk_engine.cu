@@ -54,6 +54,8 @@ struct ExpandGroup {
   bool cols = false; PkXcParams xc; unsigned xc_gx = 0; size_t xc_smem = 0;
   // bulk-store variant of it (opt-in): whole intervals per block, image handed to the TMA engine
   bool bulk = false; int xb_per_block = 0; unsigned xb_gx = 0; size_t xb_smem = 0;
+  // batches of small problems: parameter-driven, (instance, pair) space flattened over the grid
+  bool batch = false; unsigned xbt_gx = 0;
 };
 
 struct ModeState {
@@ -81,7 +83,6 @@ struct ModeState {
   int* gen_job = nullptr; int* gen_chunk = nullptr; long long gen_blocks = 0;
   std::vector<ExpandGroup> exp;  // block expansion, one launch per group
   long long max_defect_rows = 0, max_grad_count = 0, max_reduce_len = 0;
-  size_t def_smem = 0;
   double* red_partial = nullptr; unsigned* red_ticket = nullptr; int red_parts = 0;
   bool def_fast = false, def_table = false;
   bool idx32 = true;  // every flattened (instance, slot) space fits 32-bit index math
@@ -432,13 +433,27 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
   const size_t xsm = sizeof(double) * (size_t)(n0 * r0 + (PK_XC_THREADS / n0 + 2) * r0);
   bool cols = g.uniform && count <= PK_XC_JOBS && n_lists <= PK_XC_LISTS && max_pairs >= 8 * PK_XC_THREADS &&
               e->dims.batch <= 65535 && xsm <= 200 * 1024;
+  // batches of small problems (too few pairs per instance for the kernel above): the same parameter block
+  // can drive pk_expand_batch over the flattened (instance, pair) space.  Opt-in (POCKIT_B200_EXPAND=batch):
+  // measured on B200 (round 2, quadrotor B = 8192) it is SLOWER than the persistent kernel -- Jacobian
+  // expansion 79.3 vs 68.8 us, set 306 vs 297 us -- the per-thread divisions and L1 operand loads cost
+  // more than the per-block prologue it removes.
+  const bool batch_fits = !cols && g.uniform && count <= PK_XC_JOBS && n_lists <= PK_XC_LISTS && e->dims.batch > 1 &&
+                          max_pairs * e->dims.batch >= 8 * PK_XC_THREADS && max_pairs * e->dims.batch < (1LL << 32);
+  bool batch = false;
   if (const char* env = getenv("POCKIT_B200_EXPAND")) {
     if (!strcmp(env, "params") && !cols) return fail("POCKIT_B200_EXPAND=params: jobs do not fit the parameter-driven kernel");
+    if (!strcmp(env, "batch")) {
+      if (!batch_fits) return fail("POCKIT_B200_EXPAND=batch: jobs do not fit the batch kernel");
+      batch = true;
+    }
     if (!strcmp(env, "columns")) cols = false;
     if (!strcmp(env, "bulk") && !cols) return fail("POCKIT_B200_EXPAND=bulk: jobs do not fit the parameter-driven kernel");
   }
-  if (cols) {
-    g.cols = true;
+  if (cols || batch) {
+    g.cols = cols;
+    g.batch = batch;
+    g.xbt_gx = (unsigned)((max_pairs * e->dims.batch + PK_XC_THREADS - 1) / PK_XC_THREADS);
     g.xc_smem = xsm;
     PkXcParams& q = g.xc;
     memset(&q, 0, sizeof(q));
@@ -461,7 +476,7 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
     auto kern = g.lam ? (const void*)pk_expand_cols<true> : (const void*)pk_expand_cols<false>;
     if (xsm > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
     if (const char* env = getenv("POCKIT_B200_EXPAND")) {
-      if (!strcmp(env, "bulk") && n0 <= PK_XB_THREADS) {  // TMA bulk-store variant, same parameters
+      if (cols && !strcmp(env, "bulk") && n0 <= PK_XB_THREADS) {  // TMA bulk-store variant, same parameters
         const long long per = PK_XB_THREADS / n0, bn0 = n0 * r0;
         const size_t bsm = sizeof(double) * (size_t)(((bn0 + 1) & ~1LL) + ((per * r0 + 1) & ~1LL) + per * bn0 + 2);
         if (bsm <= 200 * 1024) {
@@ -603,17 +618,10 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     const long long r = jb.i[4] * jb.i[3];
     if (r > ms.max_defect_rows) ms.max_defect_rows = r;
     if (jb.i[13]) {
-      const size_t sm = sizeof(double) * (size_t)(jb.flags * (jb.i[13] | 1));
-      if (sm > ms.def_smem) ms.def_smem = sm;
       ms.def_fast = true;
     } else {
       ms.def_table = true;
     }
-  }
-  if (ms.def_smem > 48 * 1024) {
-    if (ms.def_smem > 200 * 1024) return fail("integration block too large for shared memory");
-    CK(cudaFuncSetAttribute(pk_defects_blocks<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.def_smem));
-    CK(cudaFuncSetAttribute(pk_defects_blocks<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms.def_smem));
   }
   for (long long j = 0; j < d->n_jobs[PK_STAGE_REDUCE]; ++j) {
     const long long len = d->jobs[PK_STAGE_REDUCE][j].i[3] - d->jobs[PK_STAGE_REDUCE][j].i[2];
@@ -669,6 +677,12 @@ static void launch_expand(const ModeState& ms, const PkCtx& cx, int B, cudaStrea
         pk_expand_bulk<true><<<grid, PK_XB_THREADS, g.xb_smem, st>>>(cx, g.xc, g.xb_per_block);
       else
         pk_expand_bulk<false><<<grid, PK_XB_THREADS, g.xb_smem, st>>>(cx, g.xc, g.xb_per_block);
+    } else if (g.batch) {
+      const dim3 grid(g.xbt_gx, (unsigned)g.xc.n_lists);
+      if (g.lam)
+        pk_expand_batch<true><<<grid, PK_XC_THREADS, 0, st>>>(cx, g.xc, (unsigned)B);
+      else
+        pk_expand_batch<false><<<grid, PK_XC_THREADS, 0, st>>>(cx, g.xc, (unsigned)B);
     } else if (g.cols) {
       const dim3 grid(g.xc_gx, (unsigned)g.xc.n_lists, B);
       if (g.lam)
@@ -756,9 +770,9 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
     }
     if (ms.def_fast) {
       if (ms.idx32)
-        pk_defects_blocks<unsigned><<<grid, PK_THREADS, ms.def_smem, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+        pk_defects_blocks<unsigned><<<grid, PK_THREADS, 0, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
       else
-        pk_defects_blocks<unsigned long long><<<grid, PK_THREADS, ms.def_smem, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
+        pk_defects_blocks<unsigned long long><<<grid, PK_THREADS, 0, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)ms.n_jobs[PK_STAGE_DEFECT], B);
       ++e->launches;
     }
     tr(e, mode, PK_STAGE_DEFECT, 1, a1);
@@ -1257,7 +1271,8 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
         CK(cudaGraphGetNodes(graph, nullptr, &n_nodes));
         std::vector<cudaGraphNode_t> nodes(n_nodes);
         if (n_nodes) CK(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
-        const void* big[] = {(const void*)pk_expand_cols<true>, (const void*)pk_expand_cols<false>, (const void*)pk_expand_blocks};
+        const void* big[] = {(const void*)pk_expand_cols<true>, (const void*)pk_expand_cols<false>, (const void*)pk_expand_blocks,
+                             (const void*)pk_expand_batch<true>, (const void*)pk_expand_batch<false>};
         for (cudaGraphNode_t nd : nodes) {
           cudaGraphNodeType ty;
           if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
@@ -1456,7 +1471,7 @@ extern "C" int pk_x_uploads(pk_engine* e, int64_t* count) {
 extern "C" int pk_expand_variant(pk_engine* e, int mode, int* variant) {
   if (!e || !variant || mode < 0 || mode >= PK_N_MODES) return fail("pk_expand_variant: bad argument");
   const ModeState& ms = e->mode[mode];
-  *variant = ms.exp.empty() ? 0 : (ms.exp.back().bulk ? 3 : (ms.exp.back().cols ? 2 : 1));
+  *variant = ms.exp.empty() ? 0 : (ms.exp.back().bulk ? 3 : (ms.exp.back().cols ? 2 : (ms.exp.back().batch ? 4 : 1)));
   return 0;
 }
 

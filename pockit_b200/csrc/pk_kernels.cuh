@@ -24,7 +24,7 @@
 //            i5 ipool row_ptr, i6 ipool cols, i7 dpool data (full operator, row-major),
 //            i8 ipool +1 column per row, i9 ipool -1 column per row, i10 W base of f_0 (rows consecutive),
 //            i11 scalar header (dt, front values, back values), i12 first output row,
-//            i13 n | 0, flags rows per block, i14 dpool unit block, i15 dpool widths (same-order fast path)
+//            i13 n | 0, flags rows per block, i14 dpool unit block (column-major), i15 dpool widths (same-order fast path)
 //   GENERIC  i0 dst, i1 count, i2 lam row offset (-1: none), i3 system scalar slot (-1: none),
 //            i4 post factor (0 none, 1 sigma, 2 lam[i5]), f0 sign
 //     CONST         i6 dpool values
@@ -180,18 +180,19 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects(PkCtx cx, const pk_job*
 
 // Same-order meshes: the operator is never read from memory.  i13 = n (points per interval),
 // flags = rows per block (= node step = offset of the -1 column: n-1 for LGL, n for LGR),
-// i14 dpool unit block (rows x n), i15 dpool interval widths.  Entries are (unit * width) / 2.
+// i14 dpool unit block stored COLUMN-major (n x rows: entry [c * rows + r]), i15 dpool interval widths.
+// Entries are (unit * width) / 2.  The unit block is read through L1 (__ldg): consecutive lanes own
+// consecutive rows, so for a given column they read consecutive doubles -- one or two wavefronts, no
+// shared-memory staging and no barrier.  (Round 1 staged the block in shared memory behind a
+// __syncthreads; with batches of small problems -- 8192 instances x 420 rows -- that exposed a
+// ~1 us prologue in each of 13 k short blocks: quadrotor B = 8192 constraints 41.5 us.)
 template <typename IT>  // unsigned (fast 32-bit index math) whenever rows * n_x * B < 2^32
 __global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
-  extern __shared__ double unit_s[];
   const pk_job& jb = jobs[blockIdx.y];
   const int n = (int)jb.i[13];
   if (!n) return;
   const int rb = jb.flags;
-  const int ld = n | 1;  // odd row stride: conflict-free when consecutive lanes walk consecutive rows
-  const double* unit = cx.dpool + jb.i[14];
-  for (int t = threadIdx.x; t < rb * n; t += PK_THREADS) unit_s[(t / n) * ld + (t % n)] = unit[t];
-  __syncthreads();
+  const double* __restrict__ uT = cx.dpool + jb.i[14];
   const IT rows = (IT)jb.i[4], n_x = (IT)jb.i[3];
   const IT gid = (IT)blockIdx.x * (IT)PK_THREADS + threadIdx.x;
   if (gid >= rows * n_x * (IT)B) return;
@@ -206,17 +207,17 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const 
   const double* xv = cx.X + (long long)b * cx.L + jb.i[0] + (long long)i * Lx;
   const double* f = cx.W + jb.i[10] + ((long long)i * B + b) * Lm + (long long)K * rb;
   const double w = cx.dpool[jb.i[15] + K];
-  const double* u = unit_s + rr * ld;
+  const double* u = uT + rr;
   double acc = 0.0;
 #pragma unroll 4
-  for (int c = 0; c < n; ++c) acc += ((u[c] * w) / 2.0) * f[c];
+  for (int c = 0; c < n; ++c) acc += ((__ldg(u + c * rb) * w) / 2.0) * f[c];
   const long long cp = (long long)K * rb + rr, cn = (long long)K * rb + rb;
   const double xp = cp == 0 ? Sb[1 + i] : (cp == Lx - 1 ? Sb[1 + n_x + i] : xv[cp]);
   const double xn = cn == 0 ? Sb[1 + i] : (cn == Lx - 1 ? Sb[1 + n_x + i] : xv[cn]);
   double tx = 0.0;
   tx += 1.0 * xp;
   tx += -1.0 * xn;
-  cx.OUT[(long long)b * cx.n_out + jb.i[12] + (long long)i * (long long)rows + (long long)r] = tx - acc * Sb[0];
+  pk_store(cx.OUT + (long long)b * cx.n_out + jb.i[12] + (long long)i * (long long)rows + (long long)r, tx - acc * Sb[0], cx.stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -352,6 +353,41 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
   for (int r = 0; r < rows; ++r) {
     double v = (u[r * n] * w) / 2.0;
     if (LAM) v = v * lm[r];
+    pk_store(out + r * n, v * sv, cx.stream);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Parameter-driven column walk for BATCHES of small problems (BASELINE configs[4]: 8192 instances of
+// a 14-interval mesh, 72 (interval, column) pairs per job).  pk_expand_blocks gives every instance its
+// own block (blockIdx.y), whose few warps each pay the chain job record -> list table -> list value
+// before the first store, behind a barrier for the staged unit block: ~8 k short, latency-bound blocks
+// (ncu, round 2: 66 us for the 189 MB of the quadrotor Jacobian, 2.9 TB/s).  Here the (instance, pair)
+// space of a list is flattened over the grid, geometry and list table sit in the kernel parameters
+// (constant bank), and the tiny unit block / multipliers are read through L1 (consecutive lanes ->
+// consecutive columns of one interval: coalesced or broadcast), so there is no shared memory and no
+// barrier.  Same arithmetic and association as the other expansion kernels (bit-identical results).
+template <bool LAM>
+__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B) {
+  const int n = prm.n, rows = prm.rows;
+  const int bn = n * rows;
+  const PkXcList& L = prm.list[blockIdx.y];
+  const PkXcJob& J = prm.job[L.job];
+  const unsigned t = blockIdx.x * PK_XC_THREADS + threadIdx.x;  // B * pairs < 2^32 (checked at set-up)
+  if (t >= J.pairs * B) return;
+  const unsigned b = t / J.pairs;
+  const unsigned tp = t - b * J.pairs;
+  const unsigned K = tp / (unsigned)n;
+  const unsigned cc = tp - K * (unsigned)n;
+  const double sv = cx.W[L.wbase + (long long)b * J.Lm + J.node0 + (long long)K * J.step + cc];
+  const double w = cx.dpool[J.width + K];
+  const double* __restrict__ u = cx.dpool + prm.unit + cc;
+  const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K * rows;
+  double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + L.dst + (long long)K * bn + cc;
+#pragma unroll 4
+  for (int r = 0; r < rows; ++r) {
+    double v = ((prm.sign * __ldg(u + r * n)) * w) / 2.0;
+    if (LAM) v = v * __ldg(lam + r);
     pk_store(out + r * n, v * sv, cx.stream);
   }
 }

@@ -693,7 +693,8 @@ class DevicePlan:
 
             n = int(col.num_point[0])
             unit = _unit_integration_block(col.scheme, n)
-            fast = dict(n=n, rows_blk=unit.shape[0], unit=P.dbl(unit.ravel()), width=P.dbl(col.width))
+            # column-major for the defect kernel: lanes own consecutive rows and read one column at a time
+            fast = dict(n=n, rows_blk=unit.shape[0], unit=P.dbl(np.ascontiguousarray(unit.T).ravel()), width=P.dbl(col.width))
         return dict(
             row_ptr=P.int(row_ptr), col=P.int(cols), data=P.dbl(data), tpos=P.int(tpos), tneg=P.int(tneg), **fast
         )

@@ -7,7 +7,8 @@ those the oracle was pinned on).
     C4 rocket    LGL 2x5556x10   100 010 nodes   (two phases, FUNC-linked boundaries)
     C5 quadrotor LGL 14x6, B = 8192 instances differing in the FIXED initial state
 
-The block expansion (``phasebase.py:1120-1124, 1280-1285``) has three kernels; every test asserts
+The block expansion (``phasebase.py:1120-1124, 1280-1285``) has four kernels (the fourth,
+pk_expand_batch, is exercised by the batched test); every test asserts
 that the engine really launches the one it claims to test (``Engine.expand_kernel``):
 ``columns`` -> pk_expand_blocks (persistent), ``params`` -> pk_expand_cols (the default at these
 sizes, the kernel the bench and the roofline figure run on), ``bulk`` -> pk_expand_bulk (TMA
@@ -101,7 +102,7 @@ def test_full_size_device_resident_set_matches_oracle():
 
 
 @pytest.mark.parametrize("fastmath", [False, True])
-def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath):
+def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath, monkeypatch):
     """BASELINE configs[4] at full size: B = 8192 instances, start + U(-0.2, 0.2) with rng seed 0;
     32 sampled instances (first, last, 30 random) against an oracle built for each of them.
     ``fastmath=True`` is what the example passes to Numba (``examples/planar_quadrotor.py:59``); here it
@@ -127,11 +128,20 @@ def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath):
     sig = rng.uniform(0.5, 1.5, B)
     bs = BatchedSystem(S, fixed)
     try:
-        assert bs.engine.expand_kernel(P.HESS) == "pk_expand_blocks"  # 84 (interval, column) pairs per job, blockIdx.y = instance
+        # 72 (interval, column) pairs per job and instance: the persistent kernel, blockIdx.y = instance
+        assert bs.engine.expand_kernel(P.HESS) == "pk_expand_blocks" and bs.engine.expand_kernel(P.JAC) == "pk_expand_blocks"
         obj, grad, cons = bs.objective(X), bs.gradient(X), bs.constraints(X)
         jac, hess = bs.jacobian(X), bs.hessian(X, LAM, sig)
         r = bs.engine.evaluate(X, LAM, sig)
         assert np.array_equal(r[P.JAC], jac) and np.array_equal(r[P.HESS], hess) and np.array_equal(r[P.GRAD], grad)
+    finally:
+        bs.close()
+    # the opt-in batch kernel (flattened (instance, pair) space, parameter-driven) writes the same bits
+    monkeypatch.setenv("POCKIT_B200_EXPAND", "batch")
+    bs = BatchedSystem(S, fixed)
+    try:
+        assert bs.engine.expand_kernel(P.JAC) == "pk_expand_batch" and bs.engine.expand_kernel(P.HESS) == "pk_expand_batch"
+        assert np.array_equal(bs.jacobian(X), jac) and np.array_equal(bs.hessian(X, LAM, sig), hess)
     finally:
         bs.close()
     assert jac.shape == (B, 4321) and hess.shape == (B, 2058) and np.all(np.isfinite(hess))

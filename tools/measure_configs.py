@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Measure the five BASELINE.json configurations on one GPU (plus, through bench.py's CPU arm, the
-CPU port on a bounded sample) and print one JSON line per configuration.  Not the bench contract --
+reference / the CPU port on a bounded sample) and print one JSON line per configuration.  Not the bench contract --
 bench.py is -- this fills the table in DESIGN.md / README.md.
 
     python tools/measure_configs.py [--skip-cpu] [name ...]
@@ -115,7 +115,9 @@ def main():
             r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", CPU_WORKLOAD[name],
                                 "--cores", "1", "--steps", "3", "--warmup", "1"], capture_output=True, text=True)
             if r.returncode == 0 and r.stdout.strip():
-                line["cpu_port_sets_per_s_1core"] = json.loads(r.stdout.strip().splitlines()[-1])["value"]
+                cpu = json.loads(r.stdout.strip().splitlines()[-1])
+                line["cpu_sets_per_s_1core"] = cpu["value"]
+                line["cpu_kind"] = cpu["cpu_baseline"]["kind"]  # "reference" (oracle/_ref staged) or "port"
         print(json.dumps(line), flush=True)
         eng.close()
 

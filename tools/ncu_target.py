@@ -19,7 +19,13 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 builder, scheme, kw, B = CONFIGS[name]
 S = problems.BUILDERS[builder](importlib.import_module(f"pockit_b200.{scheme}"), **kw)
 x, lam, sigma = problems.evaluation_point(S)
-eng = Engine(S.lowering)
+if B > 1:
+    import numpy as np
+    rng = np.random.default_rng(0)
+    x = x[None, :] + 1e-2 * rng.normal(size=(B, len(x)))
+    lam = np.tile(lam, (B, 1))
+    sigma = np.full(B, sigma)
+eng = Engine(S.lowering, batch=B, fastmath=S._fastmath)
 eng.upload(x, lam, sigma)
 eng.time_steps([P.OBJ, P.GRAD, P.CONS, P.JAC, P.HESS], steps, flush_l2=True)
 eng.sync()
