@@ -210,6 +210,9 @@ int pk_time(pk_engine *e, int mode, int iters, float *ms_total, float *ms_stage 
 /* one stage (bit s of stage_mask, as in pk_time) launch by launch, L2 flushed (untimed) before each:
  * the dominant kernel under the cache conditions of the whole-set measurement */
 int pk_time_stage(pk_engine *e, int mode, unsigned stage_mask, int iters, int flush_l2, float *ms_each);
+/* the same stage of several modes in turn, `rounds` times back to back (one event pair): e.g. the Jacobian
+ * and the Hessian expansion alternating as inside a set, outputs together larger than L2 */
+int pk_time_stage_alternating(pk_engine *e, const int *modes, int n_modes, unsigned stage_mask, int rounds, float *ms_total);
 /* device-resident throughput: `steps` times { [flush L2, untimed]; event; pk_run_set(modes); event };
  * ms_steps[s] is the CUDA-event time of step s on the engine stream */
 int pk_time_steps(pk_engine *e, const int *modes, int n_modes, int steps, int flush_l2, float *ms_steps);

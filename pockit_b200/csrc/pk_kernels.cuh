@@ -26,7 +26,7 @@
 //            i11 scalar header (dt, front values, back values), i12 first output row,
 //            i13 n | 0, flags rows per block, i14 dpool unit block (column-major), i15 dpool widths (same-order fast path)
 //   GENERIC  i0 dst, i1 count, i2 lam row offset (-1: none), i3 system scalar slot (-1: none),
-//            i4 post factor (0 none, 1 sigma, 2 lam[i5]), f0 sign
+//            i4 post factor (0 none, 1 sigma, 2 lam[i5]), f0 sign, i15 division multiplier of count (set by the engine)
 //     CONST         i6 dpool values
 //     KRON          i6 dpool data[a], i7 nb, i8 first scalar slot (nb consecutive), i9 ipool lam rows[a] (F_LAM)
 //     EXPAND_TABLE  i6 ipool rows, i7 ipool cols, i8 dpool data, i9 W base, i10 L_m
@@ -36,7 +36,7 @@
 //   EXPAND   i0 ipool list table (dst, W row base) x i1 lists, i2 lam row of the first block row (-1),
 //            i3 n (block columns), i4 block rows,
 //            i5 node step per interval, i6 first node, i7 dpool unit block, i8 dpool widths, i9 W base, i10 L_m,
-//            i11 (interval, column) pairs = intervals * n, f0 sign
+//            i11 (interval, column) pairs = intervals * n, f0 sign, i12 / i13 division multipliers of pairs / n (set by the engine)
 //   GRAD_RANGE   i0 dst, i1 count, i2 ipool contributions (W base, L_m, c_lo, system slot) x i3
 //   GRAD_SCALAR  i0 dst, i2 ipool contributions (scalar slot | -1, system slot) x i3
 #pragma once
@@ -63,6 +63,12 @@
 __device__ __forceinline__ void pk_store(double* p, double v, int stream) {
   if (stream) __stcs(p, v);
   else *p = v;
+}
+
+// floor(x / d) for x, d < 2^32 with the pre-computed multiplier m = floor(2^64 / d) + 1 (0 encodes d == 1);
+// the engine patches m into the job records at load time (pk_engine_load_mode) or passes it as an argument.
+__device__ __forceinline__ unsigned pk_div(unsigned x, unsigned long long m) {
+  return m ? (unsigned)__umul64hi((unsigned long long)x, m) : x;
 }
 
 struct PkCtx {
@@ -179,45 +185,61 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects(PkCtx cx, const pk_job*
 }
 
 // Same-order meshes: the operator is never read from memory.  i13 = n (points per interval),
-// flags = rows per block (= node step = offset of the -1 column: n-1 for LGL, n for LGR),
-// i14 dpool unit block stored COLUMN-major (n x rows: entry [c * rows + r]), i15 dpool interval widths.
-// Entries are (unit * width) / 2.  The unit block is read through L1 (__ldg): consecutive lanes own
-// consecutive rows, so for a given column they read consecutive doubles -- one or two wavefronts, no
-// shared-memory staging and no barrier.  (Round 1 staged the block in shared memory behind a
-// __syncthreads; with batches of small problems -- 8192 instances x 420 rows -- that exposed a
-// ~1 us prologue in each of 13 k short blocks: quadrotor B = 8192 constraints 41.5 us.)
-template <typename IT>  // unsigned (fast 32-bit index math) whenever rows * n_x * B < 2^32
-__global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {
-  const pk_job& jb = jobs[blockIdx.y];
+// flags = rows per block rb (= node step = offset of the -1 column: n-1 for LGL, n for LGR),
+// i14 dpool unit block stored COLUMN-major (n x rows: entry [c * rb + r]), i15 dpool interval widths.
+// Entries are (unit * width) / 2.  One thread per defect row over the flattened (instance, state, row)
+// space (batches of small problems keep whole warps busy); the three index splits are multiplies by
+// pre-computed reciprocals passed as kernel arguments (FAST: everything fits 32 bits), offsets inside an
+// instance are 32-bit.  (ncu, round 2: with runtime divisions and 64-bit offsets the kernel executed 318
+// instructions per row for a 6-term row sum and was issue-bound -- quadrotor B = 8192: 41 us; a 3-D grid
+// without divisions was worse, 45 us: 49 k blocks of 70 live threads.)
+// The unit block is read through L1 (__ldg): consecutive lanes own consecutive rows, so for a given
+// column they read consecutive doubles; no shared-memory staging, no barrier.
+struct PkDefectDiv {
+  unsigned long long rows, n_x, rb;  // division multipliers (pk_div)
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const pk_job* __restrict__ jobs, int job, int B, PkDefectDiv dv) {
+  const pk_job& jb = jobs[job];
   const int n = (int)jb.i[13];
-  if (!n) return;
-  const int rb = jb.flags;
-  const double* __restrict__ uT = cx.dpool + jb.i[14];
-  const IT rows = (IT)jb.i[4], n_x = (IT)jb.i[3];
-  const IT gid = (IT)blockIdx.x * (IT)PK_THREADS + threadIdx.x;
-  if (gid >= rows * n_x * (IT)B) return;
-  const int b = (int)(gid / (rows * n_x));
-  const IT rem = gid - (IT)b * rows * n_x;
-  const int i = (int)(rem / rows);
-  const IT r = rem - (IT)i * rows;
-  const IT K = r / (IT)rb;
-  const int rr = (int)(r - K * (IT)rb);
-  const long long Lx = jb.i[1], Lm = jb.i[2];
-  const double* Sb = cx.S + (long long)b * cx.n_scalar + jb.i[11];
-  const double* xv = cx.X + (long long)b * cx.L + jb.i[0] + (long long)i * Lx;
-  const double* f = cx.W + jb.i[10] + ((long long)i * B + b) * Lm + (long long)K * rb;
+  const unsigned rb = (unsigned)jb.flags;
+  const unsigned rows = (unsigned)jb.i[4], n_x = (unsigned)jb.i[3];
+  unsigned b, i, r, K;
+  if (FAST) {
+    const unsigned gid = blockIdx.x * PK_THREADS + threadIdx.x;
+    if (gid >= rows * n_x * (unsigned)B) return;
+    const unsigned pair = pk_div(gid, dv.rows);  // (instance, state)
+    r = gid - pair * rows;
+    b = pk_div(pair, dv.n_x);
+    i = pair - b * n_x;
+    K = pk_div(r, dv.rb);
+  } else {
+    const unsigned long long gid = blockIdx.x * (unsigned long long)PK_THREADS + threadIdx.x;
+    if (gid >= (unsigned long long)rows * n_x * (unsigned long long)B) return;
+    const unsigned long long pair = gid / rows;
+    r = (unsigned)(gid - pair * rows);
+    b = (unsigned)(pair / n_x);
+    i = (unsigned)(pair - (unsigned long long)b * n_x);
+    K = r / rb;
+  }
+  const unsigned rr = r - K * rb;
+  const unsigned Lx = (unsigned)jb.i[1], Lm = (unsigned)jb.i[2];
+  const double* __restrict__ Sb = cx.S + (long long)b * cx.n_scalar + jb.i[11];
+  const double* __restrict__ xv = cx.X + (long long)b * cx.L + jb.i[0] + (long long)i * Lx;
+  const double* __restrict__ f = cx.W + jb.i[10] + ((long long)i * B + b) * Lm + K * rb;
   const double w = cx.dpool[jb.i[15] + K];
-  const double* u = uT + rr;
+  const double* __restrict__ u = cx.dpool + jb.i[14] + rr;
   double acc = 0.0;
 #pragma unroll 4
   for (int c = 0; c < n; ++c) acc += ((__ldg(u + c * rb) * w) / 2.0) * f[c];
-  const long long cp = (long long)K * rb + rr, cn = (long long)K * rb + rb;
+  const unsigned cp = K * rb + rr, cn = K * rb + rb;
   const double xp = cp == 0 ? Sb[1 + i] : (cp == Lx - 1 ? Sb[1 + n_x + i] : xv[cp]);
   const double xn = cn == 0 ? Sb[1 + i] : (cn == Lx - 1 ? Sb[1 + n_x + i] : xv[cn]);
   double tx = 0.0;
   tx += 1.0 * xp;
   tx += -1.0 * xn;
-  pk_store(cx.OUT + (long long)b * cx.n_out + jb.i[12] + (long long)i * (long long)rows + (long long)r, tx - acc * Sb[0], cx.stream);
+  pk_store(cx.OUT + (long long)b * cx.n_out + jb.i[12] + (long long)i * rows + r, tx - acc * Sb[0], cx.stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -258,9 +280,9 @@ __global__ void __launch_bounds__(PK_THREADS) pk_expand_blocks(PkCtx cx, const p
     const int n = (int)jb.i[3], rows = (int)jb.i[4];
     const unsigned pairs = (unsigned)jb.i[11];
     const unsigned v = (unsigned)(uidx - prefix[j]);
-    const unsigned l = v / pairs;
+    const unsigned l = pk_div(v, (unsigned long long)jb.i[12]);  // v / pairs (multipliers patched in at load time)
     const unsigned t = v - l * pairs;
-    const unsigned K = t / (unsigned)n;
+    const unsigned K = pk_div(t, (unsigned long long)jb.i[13]);  // t / n
     const unsigned cc = t - K * (unsigned)n;
     const long long* __restrict__ lists = cx.ipool + jb.i[0] + 2 * (long long)l;  // (dst, W row base)
     const double sv = cx.W[lists[1] + (long long)b * jb.i[10] + jb.i[6] + (long long)K * jb.i[5] + cc];
@@ -479,7 +501,18 @@ __device__ __forceinline__ double pk_list_at(const PkCtx& cx, const double* Sb, 
 
 // The (instance, slot) space of a job is flattened: idx = b * count + e, so that batches of small
 // problems (runs of a few dozen slots) still fill whole warps; consecutive lanes write consecutive
-// slots of a run and continue in the next instance's run.
+// slots of a run and continue in the next instance's run.  idx -> (b, e) is a multiply by the
+// pre-computed reciprocal of count (i15, patched in at load time) on the 32-bit path; the two job types
+// that carry most slots -- constants of T, table-driven expansion of the irregular first / last
+// interval -- have their own loops without the per-slot scalar-table / post-factor set-up.
+// (ncu, round 2: the one-loop version executed 112 instructions per slot and was issue-bound.)
+template <typename IT>
+__device__ __forceinline__ void pk_split(IT idx, IT count, unsigned long long magic, unsigned& b, IT& e) {
+  if (sizeof(IT) == 4) b = pk_div((unsigned)idx, magic);
+  else b = (unsigned)(idx / count);
+  e = idx - (IT)b * count;
+}
+
 template <typename IT>  // unsigned whenever every job has count * B < 2^32
 __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk_job* __restrict__ jobs,
                                                              const int* __restrict__ blk_job,
@@ -487,14 +520,48 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
   const pk_job& jb = jobs[blk_job[blockIdx.x]];
   const IT count = (IT)jb.i[1];
   const IT total = count * (IT)B;
+  const unsigned long long magic = (unsigned long long)jb.i[15];
   const double sign = jb.f[0];
   const bool use_lam = jb.flags & PK_F_LAM;
   const IT i0 = (IT)blk_chunk[blockIdx.x] * (IT)PK_CHUNK + threadIdx.x;
+  const int type = jb.type;
+  double* __restrict__ out0 = cx.OUT + jb.i[0];
+  if (type == PK_JOB_CONST) {
+    const double* __restrict__ src = cx.dpool + jb.i[6];
+#pragma unroll
+    for (int it = 0; it < PK_ITEMS; ++it) {
+      const IT idx = i0 + (IT)it * PK_THREADS;
+      if (idx >= total) break;
+      unsigned b; IT e;
+      pk_split<IT>(idx, count, magic, b, e);
+      pk_store(out0 + (long long)b * cx.n_out + (long long)e, __ldg(src + e), cx.stream);
+    }
+    return;
+  }
+  if (type == PK_JOB_EXPAND_TABLE) {
+    const long long* __restrict__ trow = cx.ipool + jb.i[6];
+    const long long* __restrict__ tcol = cx.ipool + jb.i[7];
+    const double* __restrict__ tdat = cx.dpool + jb.i[8];
+    const double* __restrict__ w0 = cx.W + jb.i[9];
+    const long long lm = jb.i[10];
+#pragma unroll
+    for (int it = 0; it < PK_ITEMS; ++it) {
+      const IT idx = i0 + (IT)it * PK_THREADS;
+      if (idx >= total) break;
+      unsigned b; IT e;
+      pk_split<IT>(idx, count, magic, b, e);
+      double d = sign * __ldg(tdat + e);
+      if (use_lam) d = d * cx.LAM[(long long)b * cx.m + jb.i[2] + __ldg(trow + e)];
+      pk_store(out0 + (long long)b * cx.n_out + (long long)e, d * w0[(long long)b * lm + __ldg(tcol + e)], cx.stream);
+    }
+    return;
+  }
   for (int it = 0; it < PK_ITEMS; ++it) {
     const IT idx = i0 + (IT)it * PK_THREADS;
     if (idx >= total) break;
-    const int b = (int)(idx / count);
-    const IT e = idx - (IT)b * count;
+    unsigned bu; IT e;
+    pk_split<IT>(idx, count, magic, bu, e);
+    const int b = (int)bu;
     const double* Sb = cx.S + (long long)b * cx.n_scalar;
     const double* lam = cx.LAM + (long long)b * cx.m;
     const double sysv = jb.i[3] >= 0 ? Sb[jb.i[3]] : 1.0;
@@ -502,21 +569,13 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
     if (jb.i[4] == 1) post = cx.SIG[b];
     if (jb.i[4] == 2) post = lam[jb.i[5]];
     double v;
-    switch (jb.type) {
-      case PK_JOB_CONST:
-        v = cx.dpool[jb.i[6] + e];
-        break;
+    switch (type) {
       case PK_JOB_KRON: {
         const IT nb = (IT)jb.i[7];
         const IT a = e / nb, q = e - a * nb;
         double d = cx.dpool[jb.i[6] + a];
         if (use_lam) d = d * lam[cx.ipool[jb.i[9] + a]];
         v = sign * (d * Sb[jb.i[8] + q]);
-      } break;
-      case PK_JOB_EXPAND_TABLE: {
-        double d = sign * cx.dpool[jb.i[8] + e];
-        if (use_lam) d = d * lam[jb.i[2] + cx.ipool[jb.i[6] + e]];
-        v = d * cx.W[jb.i[9] + (long long)b * jb.i[10] + cx.ipool[jb.i[7] + e]];
       } break;
       case PK_JOB_SCALED:
         v = pk_list_at(cx, Sb, b, jb.flags & PK_F_A_SCALAR, 0, jb.i[6], jb.i[7], jb.i[8], (long long)e) * sysv;
@@ -528,7 +587,7 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
         break;
       default: {  // OUTER / TRIL
         long long ia, ib;
-        if (jb.type == PK_JOB_OUTER) {
+        if (type == PK_JOB_OUTER) {
           ia = (long long)(e / (IT)jb.i[12]);
           ib = (long long)e - ia * jb.i[12];
         } else {
@@ -543,26 +602,45 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
         if (jb.i[4]) v = v * post;
       }
     }
-    pk_store(cx.OUT + (long long)b * cx.n_out + jb.i[0] + (long long)e, v, cx.stream);
+    pk_store(out0 + (long long)b * cx.n_out + (long long)e, v, cx.stream);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// gradient: each output column sums its contributions in list order (np.add.at semantics)
+// gradient: each output column sums its contributions in list order (np.add.at semantics).
+// A thread owns PK_ITEMS columns PK_THREADS apart: the chains  contribution record -> node-table value
+// of its columns are independent and in flight together (the one-column version was bound by that
+// dependent-load latency: humanoid 100 k nodes 13.4 us for 20 MB of traffic).
 template <typename IT>
 __global__ void __launch_bounds__(PK_THREADS) pk_grad_range(PkCtx cx, const pk_job* __restrict__ jobs, int B) {
   const pk_job& jb = jobs[blockIdx.y];
   const IT cnt = (IT)jb.i[1];
-  const IT gid = (IT)blockIdx.x * (IT)PK_THREADS + threadIdx.x;
-  if (gid >= cnt * (IT)B) return;
-  const int b = (int)(gid / cnt);
-  const long long e = (long long)(gid - (IT)b * cnt);
-  const double* Sb = cx.S + (long long)b * cx.n_scalar;
-  const long long* q = cx.ipool + jb.i[2];
-  double acc = 0.0;
-  for (long long n = 0; n < jb.i[3]; ++n, q += 4)
-    acc += cx.W[q[0] + (long long)b * q[1] + q[2] + e] * Sb[q[3]];
-  cx.OUT[(long long)b * cx.n_out + jb.i[0] + e] = acc;
+  const IT total = cnt * (IT)B;
+  const IT g0 = (IT)blockIdx.x * (IT)PK_CHUNK + threadIdx.x;
+  if (g0 >= total) return;
+  const long long* __restrict__ q0 = cx.ipool + jb.i[2];
+  const int n_contrib = (int)jb.i[3];
+  int b[PK_ITEMS];
+  long long e[PK_ITEMS];
+  double acc[PK_ITEMS];
+#pragma unroll
+  for (int it = 0; it < PK_ITEMS; ++it) {
+    const IT gid = g0 + (IT)it * PK_THREADS;
+    const IT g = gid < total ? gid : g0;  // dead items recompute item 0 (not stored)
+    b[it] = (int)(g / cnt);
+    e[it] = (long long)(g - (IT)b[it] * cnt);
+    acc[it] = 0.0;
+  }
+  const long long* q = q0;
+  for (int n = 0; n < n_contrib; ++n, q += 4) {
+    const long long w0 = q[0], lm = q[1], c_lo = q[2], sys = q[3];
+#pragma unroll
+    for (int it = 0; it < PK_ITEMS; ++it)
+      acc[it] += cx.W[w0 + (long long)b[it] * lm + c_lo + e[it]] * cx.S[(long long)b[it] * cx.n_scalar + sys];
+  }
+#pragma unroll
+  for (int it = 0; it < PK_ITEMS; ++it)
+    if (g0 + (IT)it * PK_THREADS < total) pk_store(cx.OUT + (long long)b[it] * cx.n_out + jb.i[0] + e[it], acc[it], cx.stream);
 }
 
 __global__ void __launch_bounds__(PK_THREADS) pk_grad_scalar(PkCtx cx, const pk_job* __restrict__ jobs, int n_jobs, int B) {

@@ -112,6 +112,7 @@ def load_library():
         "pk_out_device_pointer": ([vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         "pk_time": ([vp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
         "pk_time_stage": ([vp, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
+        "pk_time_stage_alternating": ([vp, C.POINTER(C.c_int), C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "pk_time_steps": ([vp, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)], C.c_int),
         "pk_kernel_launches": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "pk_expand_variant": ([vp, C.c_int, C.POINTER(C.c_int)], C.c_int),
@@ -598,6 +599,15 @@ class Engine:
         out = (C.c_float * iters)()
         self._check(self.lib.pk_time_stage(self._h, mode, 1 << stage, iters, int(flush_l2), out))
         return list(out)
+
+    def time_stage_alternating(self, modes, stage: int, rounds: int = 20) -> float:
+        """Total CUDA-event time (ms) of ``rounds`` x (one launch of ``stage`` for every mode in turn), back to back."""
+        for m in modes:
+            self.load(m)
+        arr = (C.c_int * len(modes))(*modes)
+        total = C.c_float()
+        self._check(self.lib.pk_time_stage_alternating(self._h, arr, len(modes), 1 << stage, rounds, C.byref(total)))
+        return total.value
 
     def time_steps(self, modes, steps: int, flush_l2: bool = True):
         """Per-step CUDA-event times (ms) of running ``modes`` back to back, inputs resident in HBM."""

@@ -616,6 +616,9 @@ class DevicePlan:
                  shard: Optional[tuple] = None, node_groups: int = 1, set_subs: tuple = SET_ORDER):
         self.lo = lo
         # callbacks the set pipeline (mode SET) covers, in SET_ORDER
+        import os
+
+        self.batch_tables = os.environ.get("POCKIT_B200_BATCH_TABLES", "0") == "1"
         self.set_subs = tuple(m for m in SET_ORDER if m in set(set_subs))
         if not self.set_subs:
             raise ValueError("set_subs must name at least one callback")
@@ -757,11 +760,22 @@ class DevicePlan:
                 pieces.append(table(pending, k_end))
             pending = None
 
+        # Batches of small problems (BASELINE configs[4]: 8192 instances of a 14-interval mesh): the block
+        # kernels would give every instance its own short, latency-bound block and walk 5 x 6 blocks in
+        # 48-byte runs; the table-driven expansion of pk_generic_jobs instead flattens (instance, slot),
+        # writes fully coalesced and reads its three small per-slot tables (shared by all instances)
+        # through L1.  Used when an instance has fewer (interval, column) pairs than the parameter-driven
+        # kernel needs (1024).  Opt-in (POCKIT_B200_BATCH_TABLES=1): measured on B200 in round 2
+        # (profiles/r02_call10_small_kernels.log) the Jacobian stage is shorter (91 vs 109 us) but the whole
+        # batched set is slower (301 vs 281 us) -- three 8-byte table reads per slot load the L1 path that the
+        # other callbacks' kernels also need.
+        table_only = self.B > 1 and int(npt.sum()) < 1024 and self.batch_tables
         K = 0
         while K < nK:
             n = int(npt[K])
             rows = n - 1 if lgl else n
-            complete = K > 0 and not (lgl and K == nK - 1) and off[K + 1] - off[K] == rows * n and n <= 128
+            complete = (K > 0 and not (lgl and K == nK - 1) and off[K + 1] - off[K] == rows * n and n <= 128
+                        and not table_only)
             if not complete:
                 if pending is None:
                     pending = int(off[K])

@@ -136,12 +136,23 @@ def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath, monkeypatc
         assert np.array_equal(r[P.JAC], jac) and np.array_equal(r[P.HESS], hess) and np.array_equal(r[P.GRAD], grad)
     finally:
         bs.close()
-    # the opt-in batch kernel (flattened (instance, pair) space, parameter-driven) writes the same bits
+    # the opt-in variants: the batch kernel (flattened (instance, pair) space) writes the same bits; the
+    # table-driven route through pk_generic_jobs (POCKIT_B200_BATCH_TABLES=1: no block kernel at all) agrees
+    # to the last few ulp ((unit * width) / 2 is formed on the host there)
     monkeypatch.setenv("POCKIT_B200_EXPAND", "batch")
     bs = BatchedSystem(S, fixed)
     try:
         assert bs.engine.expand_kernel(P.JAC) == "pk_expand_batch" and bs.engine.expand_kernel(P.HESS) == "pk_expand_batch"
         assert np.array_equal(bs.jacobian(X), jac) and np.array_equal(bs.hessian(X, LAM, sig), hess)
+    finally:
+        bs.close()
+    monkeypatch.delenv("POCKIT_B200_EXPAND")
+    monkeypatch.setenv("POCKIT_B200_BATCH_TABLES", "1")
+    bs = BatchedSystem(S, fixed)
+    try:
+        assert bs.engine.expand_kernel(P.JAC) == "" and bs.engine.expand_kernel(P.HESS) == ""
+        np.testing.assert_allclose(bs.jacobian(X), jac, rtol=1e-14, atol=1e-16)
+        np.testing.assert_allclose(bs.hessian(X, LAM, sig), hess, rtol=1e-14, atol=1e-16)
     finally:
         bs.close()
     assert jac.shape == (B, 4321) and hess.shape == (B, 2058) and np.all(np.isfinite(hess))

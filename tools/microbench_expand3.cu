@@ -71,6 +71,47 @@ __global__ void __launch_bounds__(THREADS) cols_v(double* __restrict__ out_all, 
   }
 }
 
+// column walk with the rows of a block split over RS blocks (blockIdx.z): shorter blocks -> finer tail,
+// MINB = minimum resident blocks per SM asked of the compiler (register cap)
+template <bool LAMF, int THREADS, int RS, int MINB, int ST>
+__global__ void __launch_bounds__(THREADS, MINB) cols_split(double* __restrict__ out_all, const double* __restrict__ W, const double* __restrict__ LAM,
+                                                            const double* __restrict__ unit, const double* __restrict__ width, Geo g) {
+  extern __shared__ double sm[];
+  const int n = g.n, rows = g.rows, bn = n * rows;
+  const int r0 = (rows * (int)blockIdx.z) / RS, r1 = (rows * ((int)blockIdx.z + 1)) / RS;
+  const int nr = r1 - r0;
+  double* u_s = sm;                 // [nr * n] rows r0..r1 of the sign-folded unit block
+  double* lam_s = sm + nr * n;      // [(THREADS / n + 2) * nr]
+  const unsigned pairs = g.nK * n;
+  const unsigned t0 = blockIdx.x * THREADS;
+  if (t0 >= pairs) return;
+  const unsigned t = t0 + threadIdx.x;
+  const bool live = t < pairs;
+  const unsigned tt = live ? t : pairs - 1;
+  const unsigned K = tt / n, cc = tt - K * n, K0 = t0 / n;
+  const int l = blockIdx.y;
+  const double sv = W[(size_t)l * g.Lm + 1 + (size_t)K * g.step + cc];
+  const double w = width[K];
+  for (int q = threadIdx.x; q < nr * n; q += THREADS) u_s[q] = -1.0 * unit[r0 * n + q];
+  if (LAMF) {
+    unsigned tl = t0 + THREADS - 1;
+    if (tl >= pairs) tl = pairs - 1;
+    const int nKb = (int)(tl / n - K0 + 1);
+    for (int q = threadIdx.x; q < nKb * nr; q += THREADS) lam_s[q] = LAM[(size_t)(K0 + q / nr) * rows + r0 + q % nr];
+  }
+  __syncthreads();
+  if (!live) return;
+  double* __restrict__ out = out_all + list_base(g, l) + (size_t)K * bn + (size_t)r0 * n + cc;
+  const double* u = u_s + cc;
+  const double* lm = lam_s + (K - K0) * nr;
+#pragma unroll 4
+  for (int r = 0; r < nr; ++r) {
+    double v = (u[r * n] * w) / 2.0;
+    if (LAMF) v = v * lm[r];
+    store<ST>(out + r * n, v * sv);
+  }
+}
+
 template <bool LAMF>
 __global__ void __launch_bounds__(128) cols(double* __restrict__ out_all, const double* __restrict__ W, const double* __restrict__ LAM,
                                             const double* __restrict__ unit, const double* __restrict__ width, Geo g) {
@@ -340,6 +381,26 @@ static void study(const char* name, int n, int rows, int step, unsigned nK, int 
       COLSV(128, 4, 2, "cols st.wt");
       COLSV(128, 4, 3, "cols st.cg");
       COLSV(64, 10, 1, "cols 64 threads unroll 10 st.cs");
+#define COLSS(T, RS, MINB, ST, label)                                                          \
+  {                                                                                            \
+    const int nrmax = (rows + RS - 1) / RS + 1;                                                \
+    const size_t vsm = 8 * (size_t)(nrmax * n + (T / n + 2) * nrmax);                          \
+    auto lf = [&](int w) {                                                                     \
+      dim3 grid((pairs + T - 1) / T, lists, RS);                                               \
+      if (lamf) cols_split<true, T, RS, MINB, ST><<<grid, T, vsm>>>(buf[w], W, LAM, unit, width, g); \
+      else cols_split<false, T, RS, MINB, ST><<<grid, T, vsm>>>(buf[w], W, LAM, unit, width, g);     \
+    };                                                                                         \
+    cudaMemset(buf[0], 0, 8 * slots);                                                          \
+    us = timeit(lf, iters);                                                                    \
+    report(label, us, true);                                                                   \
+  }
+      COLSS(128, 1, 16, 1, "split 1 (regs<=32) st.cs");
+      COLSS(128, 2, 16, 1, "split 2 st.cs");
+      COLSS(128, 4, 16, 1, "split 4 st.cs");
+      COLSS(128, 5, 16, 1, "split 5 st.cs");
+      COLSS(64, 2, 32, 1, "split 2, 64 threads st.cs");
+      COLSS(256, 4, 8, 1, "split 4, 256 threads st.cs");
+      COLSS(128, 2, 16, 0, "split 2 plain stores");
       if (getenv("MB_COLS_ONLY")) continue;
 #define FLAT(SMV, GPT, label)                                                                  \
   {                                                                                            \
