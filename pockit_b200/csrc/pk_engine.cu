@@ -442,20 +442,14 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
   bool cols = g.uniform && count <= PK_XC_JOBS && n_lists <= PK_XC_LISTS && max_pairs >= 8 * PK_XC_THREADS &&
               e->dims.batch <= 65535 && xsm <= 200 * 1024;
   // batches of small problems (too few pairs per instance for the kernel above): the same parameter block
-  // can drive pk_expand_batch over the flattened (instance, pair) space.  Opt-in (POCKIT_B200_EXPAND=batch):
-  // measured on B200 (round 2, quadrotor B = 8192) it is SLOWER than the persistent kernel -- Jacobian
-  // expansion 79.3 vs 68.8 us, set 306 vs 297 us -- the per-thread divisions and L1 operand loads cost
-  // more than the per-block prologue it removes.
-  const bool batch_fits = !cols && g.uniform && count <= PK_XC_JOBS && n_lists <= PK_XC_LISTS && e->dims.batch > 1 &&
-                          max_pairs * e->dims.batch >= 8 * PK_XC_THREADS && max_pairs * e->dims.batch < (1LL << 32);
-  bool batch = false;
+  // drives pk_expand_batch -- one thread per (instance, interval, column) of a job, the block column of
+  // every list of the job written from registers.  POCKIT_B200_EXPAND=columns forces the persistent kernel.
+  bool batch = !cols && g.uniform && count <= PK_XC_JOBS && n_lists <= PK_XC_LISTS && e->dims.batch > 1 && r0 <= PK_XM_ROWS &&
+               max_pairs * e->dims.batch >= 8 * PK_XC_THREADS && max_pairs * e->dims.batch < (1LL << 32);
   if (const char* env = getenv("POCKIT_B200_EXPAND")) {
     if (!strcmp(env, "params") && !cols) return fail("POCKIT_B200_EXPAND=params: jobs do not fit the parameter-driven kernel");
-    if (!strcmp(env, "batch")) {
-      if (!batch_fits) return fail("POCKIT_B200_EXPAND=batch: jobs do not fit the batch kernel");
-      batch = true;
-    }
-    if (!strcmp(env, "columns")) cols = false;
+    if (!strcmp(env, "batch") && !batch) return fail("POCKIT_B200_EXPAND=batch: jobs do not fit the batch kernel");
+    if (!strcmp(env, "columns")) cols = batch = false;
     if (!strcmp(env, "bulk") && !cols) return fail("POCKIT_B200_EXPAND=bulk: jobs do not fit the parameter-driven kernel");
   }
   if (cols || batch) {
@@ -466,11 +460,14 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
     PkXcParams& q = g.xc;
     memset(&q, 0, sizeof(q));
     q.n = (int)n0; q.rows = (int)r0; q.n_jobs = (int)count; q.unit = ej[0].i[7]; q.sign = ej[0].f[0];
+    q.m_n = div_multiplier((unsigned long long)n0);
     int li = 0;
     for (int j = 0; j < q.n_jobs; ++j) {
       const pk_job& jb = ej[j];
       q.job[j].lam0 = jb.i[2]; q.job[j].node0 = jb.i[6]; q.job[j].width = jb.i[8]; q.job[j].Lm = jb.i[10];
       q.job[j].step = (int)jb.i[5]; q.job[j].pairs = (unsigned)jb.i[11];
+      q.job[j].m_pairs = div_multiplier((unsigned long long)jb.i[11]);
+      q.job[j].list0 = li; q.job[j].n_lists = (int)jb.i[1];
       for (long long l = 0; l < jb.i[1]; ++l, ++li) {
         const size_t at = (size_t)(jb.i[0] + 2 * l);
         if (at + 1 >= e->h_ipool.size()) return fail("expand job: list table outside the integer pool");
@@ -697,7 +694,9 @@ static void launch_expand(const ModeState& ms, const PkCtx& cx, int B, cudaStrea
       else
         pk_expand_bulk<false><<<grid, PK_XB_THREADS, g.xb_smem, st>>>(cx, g.xc, g.xb_per_block);
     } else if (g.batch) {
-      const dim3 grid(g.xbt_gx, (unsigned)g.xc.n_lists);
+      unsigned groups = 0;
+      for (int j = 0; j < g.xc.n_jobs; ++j) groups += (unsigned)((g.xc.job[j].n_lists + PK_XM_LISTS - 1) / PK_XM_LISTS);
+      const dim3 grid(g.xbt_gx, groups);
       if (g.lam)
         pk_expand_batch<true><<<grid, PK_XC_THREADS, 0, st>>>(cx, g.xc, (unsigned)B);
       else

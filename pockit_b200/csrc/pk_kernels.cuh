@@ -322,6 +322,8 @@ struct PkXcJob {
   long long Lm;      // nodes per W row
   int step;          // nodes per interval step
   unsigned pairs;    // intervals * n
+  unsigned long long m_pairs;  // division multiplier of pairs (pk_div)
+  int list0, n_lists;          // the job's lists are prm.list[list0 .. list0 + n_lists)
 };
 struct PkXcList {
   long long dst, wbase;
@@ -331,6 +333,7 @@ struct PkXcParams {
   int n, rows, n_lists, n_jobs;
   long long unit;  // dpool offset of the unit block
   double sign;
+  unsigned long long m_n;  // division multiplier of n
   PkXcJob job[PK_XC_JOBS];
   PkXcList list[PK_XC_LISTS];
 };
@@ -380,37 +383,62 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Parameter-driven column walk for BATCHES of small problems (BASELINE configs[4]: 8192 instances of
-// a 14-interval mesh, 72 (interval, column) pairs per job).  pk_expand_blocks gives every instance its
-// own block (blockIdx.y), whose few warps each pay the chain job record -> list table -> list value
-// before the first store, behind a barrier for the staged unit block: ~8 k short, latency-bound blocks
-// (ncu, round 2: 66 us for the 189 MB of the quadrotor Jacobian, 2.9 TB/s).  Here the (instance, pair)
-// space of a list is flattened over the grid, geometry and list table sit in the kernel parameters
-// (constant bank), and the tiny unit block / multipliers are read through L1 (consecutive lanes ->
-// consecutive columns of one interval: coalesced or broadcast), so there is no shared memory and no
-// barrier.  Same arithmetic and association as the other expansion kernels (bit-identical results).
+// Block expansion for BATCHES of small problems (BASELINE configs[4]: 8192 instances of a 14-interval
+// mesh, 72 (interval, column) pairs and 5 x 6 blocks per job).  With blocks this small the cost is index
+// arithmetic, not bytes: pk_expand_blocks executes ~260 instructions per (list, interval, column) unit
+// of 5 stores (ncu, round 2: issue-bound, 2.9 TB/s).  All lists of a job share the block geometry, the
+// unit block, the interval width and the multipliers, so a thread here owns one (instance, interval,
+// column) of a JOB, forms P[r] = ((sign * unit[r][c]) * width) / 2 [* lambda_r] ONCE in registers and then
+// writes the column of EVERY list of the job as P[r] * list value: one FP64 multiply and one store per
+// slot, ~6 instructions per slot instead of ~50.  Geometry and list table come from the kernel
+// parameters (constant bank), index splits are multiplies by pre-computed reciprocals, no shared memory,
+// no barrier.  Same association as the other expansion kernels: bit-identical results.
+// (Round 1 measured this "P in registers" shape on the one-big-mesh case -- 20 x 20 blocks, 16 lists --
+// and found it slower there: that case is bound by the store streams, this one by instruction issue.)
+#define PK_XM_ROWS 16
+#define PK_XM_LISTS 2  // lists per thread
 template <bool LAM>
 __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B) {
   const int n = prm.n, rows = prm.rows;
   const int bn = n * rows;
-  const PkXcList& L = prm.list[blockIdx.y];
-  const PkXcJob& J = prm.job[L.job];
+  // blockIdx.y enumerates (job, group of PK_XM_LISTS lists): a thread writes at most PK_XM_LISTS columns, so
+  // that jobs with many lists still spread over enough threads (8 lists per thread: 590 k threads for the
+  // quadrotor Jacobian, 80 us; 2 per thread as in its Hessian: 32 us for half the bytes)
+  int jj = 0, grp = (int)blockIdx.y;
+  while (grp >= (prm.job[jj].n_lists + PK_XM_LISTS - 1) / PK_XM_LISTS) {
+    grp -= (prm.job[jj].n_lists + PK_XM_LISTS - 1) / PK_XM_LISTS;
+    ++jj;
+  }
+  const PkXcJob& J = prm.job[jj];
+  const int l_lo = J.list0 + grp * PK_XM_LISTS;
+  const int l_hi = l_lo + PK_XM_LISTS < J.list0 + J.n_lists ? l_lo + PK_XM_LISTS : J.list0 + J.n_lists;
   const unsigned t = blockIdx.x * PK_XC_THREADS + threadIdx.x;  // B * pairs < 2^32 (checked at set-up)
   if (t >= J.pairs * B) return;
-  const unsigned b = t / J.pairs;
+  const unsigned b = pk_div(t, J.m_pairs);
   const unsigned tp = t - b * J.pairs;
-  const unsigned K = tp / (unsigned)n;
+  const unsigned K = pk_div(tp, prm.m_n);
   const unsigned cc = tp - K * (unsigned)n;
-  const double sv = cx.W[L.wbase + (long long)b * J.Lm + J.node0 + (long long)K * J.step + cc];
   const double w = cx.dpool[J.width + K];
   const double* __restrict__ u = cx.dpool + prm.unit + cc;
   const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K * rows;
-  double* __restrict__ out = cx.OUT + (long long)b * cx.n_out + L.dst + (long long)K * bn + cc;
-#pragma unroll 4
-  for (int r = 0; r < rows; ++r) {
-    double v = ((prm.sign * __ldg(u + r * n)) * w) / 2.0;
-    if (LAM) v = v * __ldg(lam + r);
-    pk_store(out + r * n, v * sv, cx.stream);
+  double P[PK_XM_ROWS];
+#pragma unroll
+  for (int r = 0; r < PK_XM_ROWS; ++r) {
+    if (r < rows) {
+      double v = ((prm.sign * __ldg(u + r * n)) * w) / 2.0;
+      if (LAM) v = v * __ldg(lam + r);
+      P[r] = v;
+    }
+  }
+  const long long wofs = (long long)b * J.Lm + J.node0 + (long long)K * J.step + cc;
+  double* __restrict__ out_b = cx.OUT + (long long)b * cx.n_out + (long long)K * bn + cc;
+  for (int li = l_lo; li < l_hi; ++li) {
+    const PkXcList& L = prm.list[li];
+    const double sv = cx.W[L.wbase + wofs];
+    double* __restrict__ out = out_b + L.dst;
+#pragma unroll
+    for (int r = 0; r < PK_XM_ROWS; ++r)
+      if (r < rows) pk_store(out + r * n, P[r] * sv, cx.stream);
   }
 }
 

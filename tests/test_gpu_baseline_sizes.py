@@ -128,21 +128,22 @@ def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath, monkeypatc
     sig = rng.uniform(0.5, 1.5, B)
     bs = BatchedSystem(S, fixed)
     try:
-        # 72 (interval, column) pairs per job and instance: the persistent kernel, blockIdx.y = instance
-        assert bs.engine.expand_kernel(P.HESS) == "pk_expand_blocks" and bs.engine.expand_kernel(P.JAC) == "pk_expand_blocks"
+        # 72 (interval, column) pairs per job and instance: the batch kernel (a thread owns one (instance,
+        # interval, column) of a job and writes that block column of every list of the job from registers)
+        assert bs.engine.expand_kernel(P.HESS) == "pk_expand_batch" and bs.engine.expand_kernel(P.JAC) == "pk_expand_batch"
         obj, grad, cons = bs.objective(X), bs.gradient(X), bs.constraints(X)
         jac, hess = bs.jacobian(X), bs.hessian(X, LAM, sig)
         r = bs.engine.evaluate(X, LAM, sig)
         assert np.array_equal(r[P.JAC], jac) and np.array_equal(r[P.HESS], hess) and np.array_equal(r[P.GRAD], grad)
     finally:
         bs.close()
-    # the opt-in variants: the batch kernel (flattened (instance, pair) space) writes the same bits; the
+    # the other routes: the persistent kernel (one block per instance) writes the same bits; the
     # table-driven route through pk_generic_jobs (POCKIT_B200_BATCH_TABLES=1: no block kernel at all) agrees
     # to the last few ulp ((unit * width) / 2 is formed on the host there)
-    monkeypatch.setenv("POCKIT_B200_EXPAND", "batch")
+    monkeypatch.setenv("POCKIT_B200_EXPAND", "columns")
     bs = BatchedSystem(S, fixed)
     try:
-        assert bs.engine.expand_kernel(P.JAC) == "pk_expand_batch" and bs.engine.expand_kernel(P.HESS) == "pk_expand_batch"
+        assert bs.engine.expand_kernel(P.JAC) == "pk_expand_blocks" and bs.engine.expand_kernel(P.HESS) == "pk_expand_blocks"
         assert np.array_equal(bs.jacobian(X), jac) and np.array_equal(bs.hessian(X, LAM, sig), hess)
     finally:
         bs.close()
