@@ -151,6 +151,10 @@ int pk_eval_hessian(pk_engine *e, const double *x, const double *lambda /* [B][m
  * another callback" case costs no upload. */
 int pk_eval_set(pk_engine *e, const double *x, const double *lambda, const double *sigma, const int *modes,
                 int n_modes, double *const *outs);
+/* same, returning once everything is enqueued (results complete after pk_sync): for callers whose inputs
+ * arrive in stages -- a mesh-shard worker starts the Jacobian when x is there, the Hessian when lambda is */
+int pk_eval_set_async(pk_engine *e, const double *x, const double *lambda, const double *sigma, const int *modes,
+                      int n_modes, double *const *outs);
 
 /* ---- optional output shaping (both leave the reference pattern contract when enabled) ----
  * Mesh sharding (one fine mesh split over several GPUs): this engine was given only a

@@ -134,6 +134,9 @@ struct pk_engine {
   int chain_last = -1;
   bool chain = false;
   bool stagger = false;  // set capture: record node_done behind every mode's per-node programs
+  // modes started by pk_eval_set_async whose completion (kernels + device-to-host copy) the engine stream
+  // does not yet depend on: joined before anything that could disturb them, and by pk_sync
+  std::vector<int> pending;
 };
 
 // tag: job stage 0..5, 6 node programs, 7 system program, 8 compaction; edge 0 = before, 1 = after
@@ -871,9 +874,25 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
   return 0;
 }
 
+// Make the engine stream wait (on the device) for the asynchronously started modes: all of them, or only
+// those that read the multipliers.
+static int drain(pk_engine* e, bool only_multiplier_readers = false) {
+  std::vector<int> keep;
+  for (int m : e->pending) {
+    if (only_multiplier_readers && m != PK_MODE_HESSIAN && m != PK_MODE_SET) {
+      keep.push_back(m);
+      continue;
+    }
+    CK(cudaStreamWaitEvent(e->stream, e->mode[m].done, 0));
+  }
+  e->pending.swap(keep);
+  return 0;
+}
+
 extern "C" int pk_upload_x(pk_engine* e, const double* x) {
   if (!e || !x) return fail("pk_upload_x: null argument");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;  // running modes still read the resident x
   const size_t n = sizeof(double) * (size_t)e->dims.batch * (size_t)e->dims.L;
   // x already in page-locked memory (pk_alloc_host, or a range registered with pk_host_register such as
   // the mapping the ranks of a sharded mesh share): copy straight from it.  The caller must leave it
@@ -900,6 +919,7 @@ extern "C" int pk_upload_x(pk_engine* e, const double* x) {
 extern "C" int pk_upload_multipliers(pk_engine* e, const double* lambda, const double* sigma) {
   if (!e) return fail("pk_upload_multipliers: null engine");
   CK(cudaSetDevice(e->device));
+  if (drain(e, true)) return 1;
   const size_t B = (size_t)e->dims.batch;
   CK(cudaEventSynchronize(e->lam_done));
   if (lambda && e->dims.m > 0) {
@@ -918,11 +938,14 @@ extern "C" int pk_upload_multipliers(pk_engine* e, const double* lambda, const d
 extern "C" int pk_run(pk_engine* e, int mode) {
   if (!e || mode < 0 || mode >= PK_N_MODES) return fail("pk_run: bad argument");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   return launch_mode(e, mode, ~0u, e->stream);
 }
 
 extern "C" int pk_sync(pk_engine* e) {
   if (!e) return fail("pk_sync: null engine");
+  CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -956,6 +979,7 @@ static int download_async(pk_engine* e, int mode, double* out, cudaStream_t st) 
 extern "C" int pk_download(pk_engine* e, int mode, double* out) {
   if (!e || !out || mode < 0 || mode >= PK_N_MODES) return fail("pk_download: bad argument");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   if (download_async(e, mode, out, e->stream)) return 1;
   CK(cudaStreamSynchronize(e->stream));
   return 0;
@@ -971,6 +995,7 @@ extern "C" int pk_download_range(pk_engine* e, int mode, int64_t offset, int64_t
   if (ms.n_compact || !ms.dl_runs.empty() || ms.in_set) return fail("pk_download_range: not available with shaped outputs");
   if (offset < 0 || count < 0 || offset + count > ms.n_out) return fail("pk_download_range: range outside the output");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   if (count)
     CK(cudaMemcpy2DAsync(out, sizeof(double) * (size_t)count, ms.OUT + offset, sizeof(double) * (size_t)ms.n_out,
                          sizeof(double) * (size_t)count, (size_t)e->dims.batch, cudaMemcpyDeviceToHost, e->stream));
@@ -1080,8 +1105,25 @@ extern "C" int pk_eval_hessian(pk_engine* e, const double* x, const double* lam,
 // so the copies of the large Jacobian / Hessian value arrays overlap the other modes' compute and
 // the host blocks once.  This is the entry point of an x-keyed evaluation cache in a solver adapter
 // (Ipopt asks for f, grad f, g, J and H at the same x; ipopt.py:41-53).
+static int eval_set(pk_engine* e, const double* x, const double* lam, const double* sig, const int* modes, int n_modes,
+                    double* const* outs, bool wait);
+
 extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, const double* sig, const int* modes,
                            int n_modes, double* const* outs) {
+  return eval_set(e, x, lam, sig, modes, n_modes, outs, true);
+}
+
+// Same, but returns as soon as everything is enqueued: the results are complete after pk_sync.  A caller
+// that receives its inputs in stages (a mesh-shard worker gets x first and the multipliers a moment later)
+// starts the Jacobian and its copy while the rest is still on its way.  Host buffers passed as x / lambda
+// must stay untouched until pk_sync when they are page-locked (they are read by the copy engine directly).
+extern "C" int pk_eval_set_async(pk_engine* e, const double* x, const double* lam, const double* sig, const int* modes,
+                                 int n_modes, double* const* outs) {
+  return eval_set(e, x, lam, sig, modes, n_modes, outs, false);
+}
+
+static int eval_set(pk_engine* e, const double* x, const double* lam, const double* sig, const int* modes, int n_modes,
+                    double* const* outs, bool wait) {
   if (!e || !modes || !outs || n_modes < 1) return fail("pk_eval_set: bad argument");
   if (!x && !e->x_resident) return fail("pk_eval_set: x = NULL reuses the resident point, but none was uploaded yet");
   CK(cudaSetDevice(e->device));
@@ -1094,6 +1136,10 @@ extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, con
     hess = hess || modes[k] == PK_MODE_HESSIAN;
   }
   if (hess && (!lam || !sig)) return fail("pk_eval_set: multipliers required for the Hessian");
+  if (wait && drain(e)) return 1;
+  for (int k = 0; k < n_modes; ++k)  // a mode started again while pending: its own stream keeps the order
+    for (size_t q = 0; q < e->pending.size(); ++q)
+      if (e->pending[q] == modes[k]) { e->pending.erase(e->pending.begin() + q); break; }
   if (x && pk_upload_x(e, x)) return 1;
   if (hess && pk_upload_multipliers(e, lam, sig)) return 1;
   unsigned asked = 0;
@@ -1111,6 +1157,10 @@ extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, con
     for (int q = 0; q < n_modes; ++q)
       if (download_async(e, modes[ord[q]], outs[ord[q]], ps.stream)) return 1;
     CK(cudaEventRecord(ps.done, ps.stream));
+    if (!wait) {
+      e->pending.push_back(PK_MODE_SET);
+      return 0;
+    }
     CK(cudaStreamWaitEvent(e->stream, ps.done, 0));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
@@ -1130,15 +1180,19 @@ extern "C" int pk_eval_set(pk_engine* e, const double* x, const double* lam, con
     if (launch_mode(e, modes[k], ~0u, ms.stream)) return 1;
     if (download_async(e, modes[k], outs[k], ms.stream)) return 1;
     CK(cudaEventRecord(ms.done, ms.stream));
-    CK(cudaStreamWaitEvent(e->stream, ms.done, 0));
+    if (wait)
+      CK(cudaStreamWaitEvent(e->stream, ms.done, 0));
+    else
+      e->pending.push_back(modes[k]);  // the engine stream stays free for the next stage's uploads
   }
-  CK(cudaStreamSynchronize(e->stream));
+  if (wait) CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
 
 extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float* ms_stage) {
   if (!e || mode < 0 || mode >= PK_N_MODES || iters < 1) return fail("pk_time: bad argument");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   ScopedEvent a, b;
   CK(a.create());
   CK(b.create());
@@ -1169,6 +1223,7 @@ extern "C" int pk_time(pk_engine* e, int mode, int iters, float* ms_total, float
 extern "C" int pk_time_stage(pk_engine* e, int mode, unsigned stage_mask, int iters, int flush_l2, float* ms_each) {
   if (!e || mode < 0 || mode >= PK_N_MODES || iters < 1 || !ms_each) return fail("pk_time_stage: bad argument");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   ScopedEvent a, b;
   CK(a.create());
   CK(b.create());
@@ -1192,6 +1247,7 @@ extern "C" int pk_time_stage_alternating(pk_engine* e, const int* modes, int n_m
   for (int k = 0; k < n_modes; ++k)
     if (modes[k] < 0 || modes[k] >= PK_N_MODES || !e->mode[modes[k]].loaded) return fail("pk_time_stage_alternating: mode not loaded");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   ScopedEvent a, b;
   CK(a.create());
   CK(b.create());
@@ -1354,12 +1410,14 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
 extern "C" int pk_run_set(pk_engine* e, const int* modes, int n_modes) {
   if (!e || !modes || n_modes < 1) return fail("pk_run_set: bad argument");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   return run_set(e, modes, n_modes);
 }
 
 extern "C" int pk_time_steps(pk_engine* e, const int* modes, int n_modes, int steps, int flush_l2, float* ms_steps) {
   if (!e || !modes || n_modes < 1 || steps < 1 || !ms_steps) return fail("pk_time_steps: bad argument");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   ScopedEvent a, b;
   CK(a.create());
   CK(b.create());
@@ -1381,6 +1439,7 @@ extern "C" int pk_time_steps(pk_engine* e, const int* modes, int n_modes, int st
 extern "C" int pk_timeline(pk_engine* e, const int* modes, int n_modes, double* rows, int max_rows, int* n_rows) {
   if (!e || !modes || n_modes < 1 || !rows || !n_rows) return fail("pk_timeline: bad argument");
   CK(cudaSetDevice(e->device));
+  if (drain(e)) return 1;
   for (int k = 0; k < n_modes; ++k)
     if (modes[k] < 0 || modes[k] >= PK_N_MODES || !e->mode[modes[k]].loaded) return fail("pk_timeline: mode not loaded");
   struct Marks {  // the trace events are released on every return path

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 import weakref
 from pathlib import Path
 from typing import Optional
@@ -97,6 +98,7 @@ def load_library():
         "pk_eval_jacobian": ([vp, vp, vp], C.c_int),
         "pk_eval_hessian": ([vp, vp, vp, vp, vp], C.c_int),
         "pk_eval_set": ([vp, vp, vp, vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)], C.c_int),
+        "pk_eval_set_async": ([vp, vp, vp, vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)], C.c_int),
         "pk_engine_set_output_runs": ([vp, C.c_int, vp, C.c_int64], C.c_int),
         "pk_engine_set_compaction": ([vp, C.c_int, C.c_int64, vp, vp], C.c_int),
         "pk_out_size": ([vp, C.c_int, C.POINTER(C.c_int64)], C.c_int),
@@ -364,7 +366,9 @@ class Engine:
             raise ValueError(f"x must have {self.B * self.lowering.r_s} entries")
         return x
 
-    def _out(self, mode: int, out: Optional[np.ndarray]) -> np.ndarray:
+    def _out(self, mode: int, out: Optional[np.ndarray], small_pinned: bool = False) -> np.ndarray:
+        """Destination of a mode's values.  ``small_pinned``: page-locked even for tiny results -- a copy into
+        pageable memory blocks the host until the mode has finished, which an asynchronous call must not."""
         n = self.B * self.n_host[mode]
         if out is None:
             if self.reuse_outputs:
@@ -373,7 +377,7 @@ class Engine:
                 if mode not in self._pinned:
                     self._pinned[mode] = PinnedArray(n)
                 return self._pinned[mode].array
-            if self.pool is not None and n >= 8192:
+            if self.pool is not None and (n >= 8192 or small_pinned):
                 return self.pool.take(n)
             return np.empty(n, dtype=np.float64)
         if out.size != n or out.dtype != np.float64 or not out.flags.c_contiguous:
@@ -412,10 +416,12 @@ class Engine:
             runs = np.ascontiguousarray(runs, dtype=np.int64).reshape(-1, 2)
             self._check(self.lib.pk_engine_set_output_runs(self._h, mode, _ptr(runs), len(runs)))
 
-    def evaluate(self, x, fct_c=None, fct_o=None, modes=None, outs=None):
+    def evaluate(self, x, fct_c=None, fct_o=None, modes=None, outs=None, wait: bool = True):
         """Several callbacks at one ``x`` in a single engine call (``pk_eval_set``): ``x`` and the
         multipliers are uploaded once, the modes run concurrently and each result is copied back as
-        soon as it is ready.  Returns ``{mode: array}``; the Hessian is included when ``fct_c`` is given."""
+        soon as it is ready.  Returns ``{mode: array}``; the Hessian is included when ``fct_c`` is given.
+        ``wait=False`` (``pk_eval_set_async``) returns once everything is enqueued: the arrays are complete
+        after :meth:`sync`, and page-locked inputs must stay untouched until then."""
         if modes is None:
             modes = [P.OBJ, P.GRAD, P.CONS, P.JAC] + ([P.HESS] if fct_c is not None else [])
         modes = list(modes)
@@ -429,14 +435,22 @@ class Engine:
             if lam.size != self.B * self.lowering.m:
                 raise ValueError(f"fct_c must have {self.B * self.lowering.m} entries")
             sig = np.ascontiguousarray(np.broadcast_to(np.asarray(1.0 if fct_o is None else fct_o, dtype=np.float64), (self.B,)))
-        bufs = [self._out(m, None if outs is None else outs[k]) for k, m in enumerate(modes)]
+        bufs = [self._out(m, None if outs is None else outs[k], small_pinned=not wait) for k, m in enumerate(modes)]
         marr = (C.c_int * len(modes))(*modes)
         parr = (C.c_void_p * len(modes))(*[b.ctypes.data for b in bufs])
-        self._check(self.lib.pk_eval_set(self._h, None if x is None else _ptr(x), None if lam is None else _ptr(lam),
-                                         None if sig is None else _ptr(sig), marr, len(modes), parr))
+        call = self.lib.pk_eval_set if wait else self.lib.pk_eval_set_async
+        t0 = time.perf_counter()
+        self._check(call(self._h, None if x is None else _ptr(x), None if lam is None else _ptr(lam),
+                         None if sig is None else _ptr(sig), marr, len(modes), parr))
+        self.last_call_ms = 1e3 * (time.perf_counter() - t0)  # host time inside the C call (diagnostics)
+        if not wait:
+            self._keep = (x, lam, sig)  # the staging copies read these until sync()
         res = {}
         for m, b in zip(modes, bufs):
-            res[m] = (np.float64(b[0]) if self.B == 1 else b) if m == P.OBJ else self._shape(m, b)
+            if m == P.OBJ and self.B == 1 and wait:
+                res[m] = np.float64(b[0])
+            else:  # asynchronous call: the objective stays a one-element array, complete after sync()
+                res[m] = b if m == P.OBJ else self._shape(m, b)
         return res
 
     def objective(self, x):

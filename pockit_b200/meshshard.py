@@ -43,7 +43,10 @@ from . import plan as P
 
 __all__ = ["MeshShardedSystem"]
 
-_CTRL = 64  # int64 control words: [0] sequence, [1] command, [8+g] done sequence of rank g, [24+g] error flag
+# int64 control words: [0] sequence (x and the command are published), [1] command, [2] sequence for which the
+# multipliers are published too, [8+g] done sequence of rank g, [24+g] error flag,
+# [40+g] / [56+g] time.monotonic_ns() at which rank g saw the point / finished its share (diagnostics)
+_CTRL = 80
 _CMD_JAC, _CMD_HESS, _CMD_EXIT = 1, 2, 4
 _PAGE = 4096
 
@@ -127,6 +130,7 @@ class MeshShardedSystem:
         # its first point while this rank was still page-locking the mapping (seen at 8 ranks: a worker
         # that read 1 waited for the counter to change forever)
         self._seq = 0
+        self.last_timeline = {}
         self.pinned_outputs = False
         self._closed = False
 
@@ -144,43 +148,68 @@ class MeshShardedSystem:
         spins = 0
         while not cond():
             spins += 1
-            if spins > 2000:  # a short burst of polling (a set takes ~1 ms), then stop hogging the core:
-                # with one process per GPU the pollers otherwise compete with rank 0 for host cores
-                time.sleep(0.00002 if spins < 20000 else 0.0005)
+            if spins > 20000:  # a few milliseconds of polling (the gap between two sets of a solver), then stop
+                # hogging the core: with one process per GPU the pollers otherwise compete with rank 0 for host cores
+                time.sleep(0.00002 if spins < 200000 else 0.0005)
                 if time.perf_counter() - t0 > timeout:
                     raise TimeoutError(f"mesh shard: timed out waiting for {what}")
 
-    def _run_share(self, cmd: int, extra_modes=()):
+    def _enqueue(self, modes, outs, x_sent: bool, with_multipliers: bool):
+        """Start ``modes`` on the engine without waiting (``pk_eval_set_async``): ``x`` travels with the first
+        call of a point, later calls run at the resident copy."""
         a = self.buf.arr
-        modes, outs = list(extra_modes), [None] * len(extra_modes)
-        if cmd & _CMD_JAC:
-            modes.append(P.JAC)
-            outs.append(a["jac"][: self.nnz_jac])
-        if cmd & _CMD_HESS:
-            modes.append(P.HESS)
-            outs.append(a["hess"][: self.nnz_hess])
-        if not modes:
-            return {}
-        lam = a["lam"][: self.m] if cmd & _CMD_HESS else None
-        return self.engine.evaluate(a["x"], lam, a["sig"] if cmd & _CMD_HESS else None, modes=modes, outs=outs)
+        lam = a["lam"][: self.m] if with_multipliers else None
+        return self.engine.evaluate(None if x_sent else a["x"], lam, a["sig"] if with_multipliers else None,
+                                    modes=list(modes), outs=list(outs), wait=False)
 
-    def serve(self):
-        """Ranks > 0: evaluate this rank's share whenever rank 0 publishes a new point."""
+    def _run_share(self, cmd: int, extra_modes=(), lam_ready=None):
+        """This rank's share of one evaluation point, in two stages: everything that needs only ``x``
+        (the small callbacks on rank 0, the Jacobian share) starts as soon as ``x`` is published -- its
+        device-to-host copy is already running when the multipliers arrive (``lam_ready()`` returns, or
+        publishes them on rank 0) and the Hessian share follows.  One synchronisation at the end."""
+        a = self.buf.arr
+        res, x_sent = {}, False
+        if self.rank == 0 and lam_ready is not None:
+            lam_ready()  # the caller publishes the multipliers BEFORE its own enqueue work: the workers are waiting for them
+            lam_ready = None
+        first = list(extra_modes) + ([P.JAC] if cmd & _CMD_JAC else [])
+        if first:
+            outs = [None] * len(extra_modes) + ([a["jac"][: self.nnz_jac]] if cmd & _CMD_JAC else [])
+            t0 = time.perf_counter()
+            res.update(self._enqueue(first, outs, x_sent, False))
+            self._enqueue_ms = (1e3 * (time.perf_counter() - t0), getattr(self.engine, "last_call_ms", None))
+            x_sent = True
+        if cmd & _CMD_HESS:
+            if lam_ready is not None:
+                lam_ready()
+            res.update(self._enqueue([P.HESS], [a["hess"][: self.nnz_hess]], x_sent, True))
+        if res:
+            self.engine.sync()
+            if P.OBJ in res and np.ndim(res[P.OBJ]) and np.size(res[P.OBJ]) == 1:
+                res[P.OBJ] = np.float64(np.asarray(res[P.OBJ]).reshape(-1)[0])  # read only now: the call above was asynchronous
+        return res
+
+    def serve(self, idle_timeout: float = 600.0):
+        """Ranks > 0: evaluate this rank's share whenever rank 0 publishes a new point.  Gives up when
+        nothing arrives for ``idle_timeout`` seconds (a caller that died must not leave workers -- and
+        the GPUs they hold -- waiting forever)."""
         if self.rank == 0:
             raise RuntimeError("rank 0 is the caller, not a worker")
         ctrl = self.buf.ctrl
         while True:
-            self._wait(lambda: int(ctrl[0]) != self._seq, "the next evaluation point", timeout=float("inf"))
+            self._wait(lambda: int(ctrl[0]) != self._seq, "the next evaluation point", timeout=idle_timeout)
             self._seq = int(ctrl[0])
+            ctrl[40 + self.rank] = time.monotonic_ns()
             cmd = int(ctrl[1])
             if cmd & _CMD_EXIT:
                 break
             try:
-                self._run_share(cmd)
+                self._run_share(cmd, lam_ready=lambda: self._wait(lambda: int(ctrl[2]) == self._seq, "the multipliers", timeout=60.0))
             except Exception:
                 ctrl[24 + self.rank] = 1
                 ctrl[8 + self.rank] = self._seq
                 raise
+            ctrl[56 + self.rank] = time.monotonic_ns()
             ctrl[8 + self.rank] = self._seq
         self._release()
 
@@ -192,21 +221,37 @@ class MeshShardedSystem:
         x = np.asarray(x, dtype=np.float64)
         if x.size != self.L:
             raise ValueError(f"x must have {self.L} entries")
-        a["x"][:] = x.reshape(-1)
+        lam = None
         if cmd & _CMD_HESS:
             lam = np.asarray(fct_c, dtype=np.float64)
             if lam.size != self.m:
                 raise ValueError(f"fct_c must have {self.m} entries")
-            a["lam"][: self.m] = lam.reshape(-1)
-            a["sig"][0] = float(fct_o)
+        t = {"start": time.monotonic_ns()}
+        a["x"][:] = x.reshape(-1)
         ctrl[1] = cmd
         self._seq += 1
-        ctrl[0] = self._seq  # publish (x86: stores are not reordered with earlier stores)
-        res = self._run_share(cmd, extra_modes)
+        ctrl[0] = self._seq  # publish x (x86: stores are not reordered with earlier stores)
+        t["x_published"] = time.monotonic_ns()
+
+        def publish_multipliers():  # while this runs, every rank is already uploading x / expanding its Jacobian share
+            t["first_stage_enqueued"] = time.monotonic_ns()
+            a["lam"][: self.m] = lam.reshape(-1)
+            a["sig"][0] = float(fct_o)
+            ctrl[2] = self._seq
+            t["multipliers_published"] = time.monotonic_ns()
+
+        res = self._run_share(cmd, extra_modes, lam_ready=publish_multipliers if cmd & _CMD_HESS else None)
+        t["own_share_done"] = time.monotonic_ns()
         for g in range(1, self.world):
             self._wait(lambda g=g: int(ctrl[8 + g]) == self._seq, f"rank {g}")
             if ctrl[24 + g]:
                 raise RuntimeError(f"mesh shard: rank {g} failed")
+        t["all_done"] = time.monotonic_ns()
+        # where the time of the last point went, in ms since its start (host clock, shared by all ranks)
+        self.last_timeline = {k: (v - t["start"]) / 1e6 for k, v in t.items() if k != "start"}
+        self.last_timeline["first_enqueue_ms (python, C call)"] = getattr(self, "_enqueue_ms", None)
+        self.last_timeline["workers_saw_point"] = [(int(ctrl[40 + g]) - t["start"]) / 1e6 for g in range(1, self.world)]
+        self.last_timeline["workers_done"] = [(int(ctrl[56 + g]) - t["start"]) / 1e6 for g in range(1, self.world)]
         return res
 
     def _view(self, name: str, n: int):

@@ -127,3 +127,36 @@ def test_batched_compaction():
         want = np.add.reduceat(full[b][c["perm"]], c["ptr"][:-1])
         np.testing.assert_allclose(got[b], want, rtol=1e-12, atol=1e-13)
     bs.close()
+
+
+def test_staged_asynchronous_evaluation_matches_the_blocking_call():
+    """pk_eval_set_async: the inputs arrive in stages (x first, the multipliers later -- a mesh-shard
+    worker), every stage is enqueued without waiting and one pk_sync completes all results."""
+    import pockit_b200.radau as rad
+    from pockit_b200 import plan as P
+    from pockit_b200 import problems
+    from pockit_b200.engine import Engine
+
+    S = problems.robot_arm(rad, mesh=120, num_point=12)
+    x, lam, sigma = problems.evaluation_point(S, seed=6)
+    eng = Engine(S.lowering)
+    try:
+        want = eng.evaluate(x, lam, sigma)
+        want = {m: np.array(v, copy=True) for m, v in want.items()}
+        for trial in range(3):
+            xs = x + 1e-3 * trial
+            ref = {m: np.array(v, copy=True) for m, v in eng.evaluate(xs, lam, sigma).items()}
+            first = eng.evaluate(xs, modes=[P.OBJ, P.GRAD, P.CONS, P.JAC], wait=False)
+            second = eng.evaluate(None, lam, sigma, modes=[P.HESS], wait=False)  # at the resident x
+            assert np.ndim(first[P.OBJ]) == 1  # not read before the sync: still the one-element buffer
+            eng.sync()
+            got = {**first, **second}
+            for m in ref:
+                assert np.array_equal(np.atleast_1d(got[m]), np.atleast_1d(ref[m])), P.MODES[m]
+        # a blocking call right behind an unfinished asynchronous one is ordered correctly too
+        eng.evaluate(x, modes=[P.JAC], wait=False)
+        again = eng.evaluate(x, lam, sigma)
+        for m in want:
+            assert np.array_equal(np.atleast_1d(again[m]), np.atleast_1d(want[m])), P.MODES[m]
+    finally:
+        eng.close()

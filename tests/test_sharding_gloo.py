@@ -112,7 +112,10 @@ def _mesh_worker(rank, world, port, q):
         def __init__(self, lowering, shard):
             self.e = HostEmu(S, shard=shard)
 
-        def evaluate(self, x, fct_c=None, fct_o=None, modes=None, outs=None):
+        def evaluate(self, x, fct_c=None, fct_o=None, modes=None, outs=None, wait=True):
+            if x is not None:  # x travels with the first call of a point; later calls use the resident copy
+                self.x = np.array(x, copy=True)
+            x = self.x
             res = {}
             for k, m in enumerate(modes):
                 full = self.e.run(m, x, fct_c, None if fct_o is None else float(np.asarray(fct_o).reshape(-1)[0]))
@@ -121,6 +124,9 @@ def _mesh_worker(rank, world, port, q):
                     out[off : off + cnt] = full[off : off + cnt]
                 res[m] = out[0] if m == P.OBJ else out
             return res
+
+        def sync(self):
+            pass
 
         def objective(self, x):
             return self.e.run(P.OBJ, x)[0]
