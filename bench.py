@@ -783,6 +783,7 @@ def bench_sharded(args, S, eng, x, lam, sigma, P, peak, peak_source, clk, value,
                 ms.evaluate(x, lam, sigma)
             e2e_t = time.perf_counter() - t0
             timeline = dict(ms.last_timeline)
+            ms_rates = ms.link_rates
             r = ms.evaluate(x, lam, sigma)  # and once more after the timed loop
             mismatch += [k + " (after the timed loop)" for k in want if not np.array_equal(np.asarray(r[k]), np.asarray(want[k]))]
             exact = not mismatch
@@ -809,7 +810,8 @@ def bench_sharded(args, S, eng, x, lam, sigma, P, peak, peak_source, clk, value,
                     "api": "MeshShardedSystem.evaluate(x, lam, sigma) on rank 0: x published in a shared page-locked mapping, every rank "
                            "copies its share of the Jacobian / Hessian values back over its own PCIe link",
                     "bit_identical_to_unsharded": bool(exact), "mismatching_outputs": mismatch, "collective_in_data_path": "none",
-                    "last_set_timeline_ms": timeline},
+                    "last_set_timeline_ms": timeline,
+                    "share_weights_from_link_rates_GBps": ms_rates},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }

@@ -98,12 +98,22 @@ class MeshShardedSystem:
         self.L, self.m = lo.r_s, lo.m
         self.nnz_jac, self.nnz_hess = lo.nnz_jac, lo.nnz_hess_o + lo.nnz_hess_c
         shard = (self.rank, self.world)
+        self.link_rates = None
         if make_engine is None:
             from .engine import Engine  # raises without the CUDA library / a device
 
             if device is None:
                 device = int(os.environ.get("LOCAL_RANK", str(self.rank)))
             make_engine = lambda lowering, sh: Engine(lowering, fastmath=system._fastmath, device=device, shard=sh)  # noqa: E731
+            if self.world > 1 and os.environ.get("POCKIT_B200_MESH_WEIGHTS", "1") != "0":
+                # The path is bound by the device-to-host copies, and the ranks' links are not equally fast on
+                # every box (8 GPUs behind two uplinks: one half of the ranks finished 0.7 ms after the other):
+                # measure what every rank gets while ALL ranks copy, and size the shares accordingly.  Rank 0
+                # also carries the small callbacks and starts a little later: a slightly smaller share.
+                self.link_rates = self._measure_link_rates(device)
+                w = np.array(self.link_rates, dtype=np.float64)
+                w[0] *= 0.9
+                shard = (self.rank, self.world, w / w.sum())
         self.engine = make_engine(lo, shard)
         # rendezvous: rank 0 creates the mapping, everybody attaches, then the name is removed
         path = [f"{shm_dir}/pockit_b200_mesh_{os.getpid()}_{time.time_ns() & 0xFFFFFF:x}" if self.rank == 0 else None]
@@ -130,9 +140,38 @@ class MeshShardedSystem:
         # its first point while this rank was still page-locking the mapping (seen at 8 ranks: a worker
         # that read 1 waited for the counter to change forever)
         self._seq = 0
+        self._helper = None
+        if self.rank == 0:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._helper = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pockit_b200_publish")
         self.last_timeline = {}
         self.pinned_outputs = False
         self._closed = False
+
+    def _measure_link_rates(self, device: int, mbytes: int = 32, reps: int = 6) -> list:
+        """GB/s of device-to-host copies into page-locked memory per rank, all ranks copying at the same time
+        (collective: every rank calls it)."""
+        import torch
+        import torch.distributed as dist
+
+        n = (mbytes << 20) // 8
+        dev = torch.zeros(n, dtype=torch.float64, device=torch.device("cuda", device))
+        host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        host.copy_(dev)
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.device(device):
+            a.record()
+            for _ in range(reps):
+                host.copy_(dev, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize(device)
+        rate = reps * 8 * n / (a.elapsed_time(b) * 1e-3) / 1e9
+        rates = [None] * self.world
+        dist.all_gather_object(rates, float(rate))
+        return [float(r) for r in rates]
 
     # ------------------------------------------------------------------ structures (unchanged)
     def jacobianstructure(self):
@@ -169,9 +208,12 @@ class MeshShardedSystem:
         publishes them on rank 0) and the Hessian share follows.  One synchronisation at the end."""
         a = self.buf.arr
         res, x_sent = {}, False
+        pending_publish = None
         if self.rank == 0 and lam_ready is not None:
-            lam_ready()  # the caller publishes the multipliers BEFORE its own enqueue work: the workers are waiting for them
-            lam_ready = None
+            # the caller publishes the multipliers on a helper thread WHILE it enqueues its own first stage (the
+            # C call releases the GIL): the workers are waiting for them, and its own GPU should not wait either
+            pending_publish = self._helper.submit(lam_ready)
+            lam_ready = pending_publish.result
         first = list(extra_modes) + ([P.JAC] if cmd & _CMD_JAC else [])
         if first:
             outs = [None] * len(extra_modes) + ([a["jac"][: self.nnz_jac]] if cmd & _CMD_JAC else [])
@@ -290,6 +332,8 @@ class MeshShardedSystem:
         if self._closed:
             return
         self._closed = True
+        if self._helper is not None:
+            self._helper.shutdown(wait=True)
         if self._locked:
             try:
                 self.engine.lib.pk_host_unregister(self.buf.address)

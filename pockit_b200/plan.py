@@ -158,7 +158,7 @@ class ModePlan:
         self.grad_range = (0, 0)   # output slots the gradient gather-sums into (zeroed first)
         self._build()
         if owner.shard is not None:
-            self._shard(*owner.shard)
+            self._shard(owner.shard[0], owner.shard[1])
 
     # ---------------------------------------------------------------- allocation helpers
     def tab(self, value) -> int:
@@ -246,8 +246,17 @@ class ModePlan:
                 self.jobs = {s: [] for s in range(6)}
             return
 
+        # share boundaries: equal shares by default; with `shard = (rank, world, weights)` rank r gets a share
+        # proportional to weights[r] (the ranks' device-to-host links are not equally fast on every box, and
+        # the end-to-end path is copy-bound: meshshard measures the rates and passes them in).  Every rank
+        # derives the same boundaries from the same vector, so the shares still partition the output.
+        cum = self.owner.shard_cum
+
+        def cut(count, r):
+            return count if r >= G else (0 if r <= 0 else min(count, int(count * cum[r])))
+
         def part(count):
-            return count * g // G, count * (g + 1) // G
+            return cut(count, g), cut(count, g + 1)
 
         def clone(rec):
             r = dict(rec)
@@ -294,7 +303,7 @@ class ModePlan:
             for li in range(len(rec["lists"])):
                 tiles.append((rec, li, rec["i"][11] // n, n * rows))
         total = sum(nK * sz for _, _, nK, sz in tiles)
-        lo_w, hi_w = total * g // G, total * (g + 1) // G
+        lo_w, hi_w = cut(total, g), cut(total, g + 1)
         expand, seen = [], 0
         groups: dict = {}  # (id(job record), Ka, Kb) -> cloned record holding the lists with that range
         for rec, li, nK, sz in tiles:
@@ -630,6 +639,16 @@ class DevicePlan:
                 raise ValueError("shard must be (rank, world) with 0 <= rank < world")
             if fused:
                 raise ValueError("mesh sharding is not available with the fused expansion variant")
+            weights = np.ones(G) if len(shard) < 3 or shard[2] is None else np.asarray(shard[2], dtype=np.float64)
+            if weights.shape != (G,) or not np.all(np.isfinite(weights)) or np.any(weights <= 0):
+                raise ValueError("shard weights must be `world` positive numbers")
+            # cumulative share boundaries as exact fractions of equal weights when all weights are equal
+            if np.all(weights == weights[0]):
+                self.shard_cum = [r / G for r in range(G + 1)]
+            else:
+                c = np.concatenate([[0.0], np.cumsum(weights / weights.sum())])
+                c[-1] = 1.0
+                self.shard_cum = [float(v) for v in c]
             shard = (g, G)
         self.shard = shard
         # node_groups > 1: up to that many threads per node, one per group of functions (measured

@@ -65,3 +65,32 @@ def test_bad_shard_arguments():
         P.DevicePlan(S.lowering, shard=(2, 2))
     with pytest.raises(ValueError):
         P.DevicePlan(S.lowering, shard=(0, 2), fused=True)
+
+
+@pytest.mark.parametrize("case", ["robot_arm_lgr_6x20", "rocket_lgl_4x5", "general_lgr"])
+def test_weighted_shares_partition_and_follow_the_weights(case, monkeypatch):
+    """shard = (rank, world, weights): shares proportional to the ranks' measured device-to-host rates
+    (meshshard) must still partition the output and reassemble bit for bit."""
+    monkeypatch.setattr(P, "SPLIT_MIN", 4)
+    S, g = build(case), load(case)
+    x, lam, sigma = g["x"], g["lam"], float(g["sigma"])
+    whole = HostEmu(S)
+    w = [0.5, 1.3, 0.9, 2.0]
+    for mode, args in ((P.JAC, (x,)), (P.HESS, (x, lam, sigma)), (P.CONS, (x,))):
+        want = whole.run(mode, *args)
+        full, cover, owned = np.full(len(want), np.nan), np.zeros(len(want), dtype=np.int64), []
+        for r in range(4):
+            E = HostEmu(S, shard=(r, 4, w))
+            out = E.run(mode, *args)
+            runs = E.fin[mode]["runs"]
+            owned.append(int(sum(c for _, c in runs)))
+            for off, cnt in runs:
+                full[off : off + cnt] = out[off : off + cnt]
+                cover[off : off + cnt] += 1
+        assert np.all(cover == 1) and np.array_equal(full, want)
+        if mode != P.CONS and case == "robot_arm_lgr_6x20":  # the splittable part dominates: shares follow the weights
+            assert owned[3] > owned[1] > owned[2] > owned[0]
+    with pytest.raises(ValueError):
+        P.DevicePlan(S.lowering, shard=(0, 4, [1.0, 0.0, 1.0, 1.0]))
+    with pytest.raises(ValueError):
+        P.DevicePlan(S.lowering, shard=(0, 4, [1.0, 1.0]))
