@@ -71,6 +71,7 @@ struct ModeState {
   cudaStream_t stream = nullptr;      // used when a whole evaluation set is launched at once
   cudaEvent_t done = nullptr;
   cudaEvent_t node_done = nullptr;    // recorded behind the per-node programs when a set is staggered (run_set)
+  cudaEvent_t node_fork = nullptr, node_join[2] = {nullptr, nullptr};  // phases' per-node programs side by side
   cudaStream_t side = nullptr;        // the small slot runs overlap the block expansion
   cudaEvent_t side_fork = nullptr, side_join = nullptr;
   // two more branches of the small-kernel DAG (defects / gradient gather run beside the reduction chain)
@@ -246,6 +247,9 @@ static void free_mode(ModeState& ms) {
   if (ms.stream) cudaStreamDestroy(ms.stream);
   if (ms.done) cudaEventDestroy(ms.done);
   if (ms.node_done) cudaEventDestroy(ms.node_done);
+  if (ms.node_fork) cudaEventDestroy(ms.node_fork);
+  for (auto& ev : ms.node_join)
+    if (ev) cudaEventDestroy(ev);
   if (ms.side) cudaStreamDestroy(ms.side);
   if (ms.side_fork) cudaEventDestroy(ms.side_fork);
   if (ms.side_join) cudaEventDestroy(ms.side_join);
@@ -483,8 +487,16 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
     g.xc_gx = (unsigned)((max_pairs + PK_XC_THREADS - 1) / PK_XC_THREADS);
     auto kern = g.lam ? (const void*)pk_expand_cols<true> : (const void*)pk_expand_cols<false>;
     if (xsm > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
-    if (const char* env = getenv("POCKIT_B200_EXPAND")) {
-      if (cols && !strcmp(env, "bulk") && n0 <= PK_XB_THREADS) {  // TMA bulk-store variant, same parameters
+    // TMA bulk-store variant (same parameters): chosen when the interval blocks are NOT a whole number of
+    // 32-byte sectors (LGL n = 10: 90 slots), where the column walk's 8-byte stores straddle sectors whatever
+    // the base alignment; the bulk copy of a shared-memory image writes whole sectors.  Measured on B200
+    // (round 2, profiles/r02_call15_bulk_lgl.log): humanoid set 128.7 -> 121.4 us, rocket 56.5 -> 55.5; on the
+    // sector-aligned 20 x 20 blocks of robot_arm it is slower (56.7 -> 62.8), so the column walk stays there.
+    // POCKIT_B200_EXPAND=bulk forces it, =params forbids it.
+    {
+      const char* env = getenv("POCKIT_B200_EXPAND");
+      const bool want_bulk = env ? !strcmp(env, "bulk") : (((n0 * r0) & 3) != 0 && e->dims.batch == 1);
+      if (cols && want_bulk && n0 <= PK_XB_THREADS) {
         const long long per = PK_XB_THREADS / n0, bn0 = n0 * r0;
         const size_t bsm = sizeof(double) * (size_t)(((bn0 + 1) & ~1LL) + ((per * r0 + 1) & ~1LL) + per * bn0 + 2);
         if (bsm <= 200 * 1024) {
@@ -586,6 +598,8 @@ extern "C" int pk_engine_load_mode(pk_engine* e, int mode, const pk_mode_desc* d
     CK(cudaStreamCreateWithPriority(&ms.stream, cudaStreamNonBlocking, use_prio && !big ? prio_hi : prio_lo));
     CK(cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ms.node_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ms.node_fork, cudaEventDisableTiming));
+    for (auto& ev : ms.node_join) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CK(cudaStreamCreateWithPriority(&ms.side, cudaStreamNonBlocking, use_prio ? prio_hi : prio_lo));
     CK(cudaEventCreateWithFlags(&ms.side_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ms.side_join, cudaEventDisableTiming));
@@ -732,6 +746,15 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
   auto on = [&](int stage) { return (stage_mask & (1u << stage)) != 0; };
   if (on(PK_N_STAGES)) {
     tr(e, mode, 6, 0, st);
+    // The per-node programs of the phases of a multi-phase system are independent (they write disjoint
+    // table rows / scalar slots): phases 1, 2, ... run beside phase 0 on the auxiliary streams and are joined
+    // before anything reads their results (two-stage rocket: 2 x 50 k nodes, each program latency-bound).
+    const bool spread = stage_mask == ~0u && ms.node_kernels.size() > 1 && !e->trace;
+    if (spread) {
+      CK(cudaEventRecord(ms.node_fork, st));
+      CK(cudaStreamWaitEvent(ms.aux1, ms.node_fork, 0));
+      if (ms.node_kernels.size() > 2) CK(cudaStreamWaitEvent(ms.aux2, ms.node_fork, 0));
+    }
     for (size_t p = 0; p < ms.node_kernels.size(); ++p) {
       const pk_node_program& np_ = ms.node_programs[p];
       const double* tm = e->dpool + np_.tm_offset;
@@ -739,8 +762,17 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
       int Bi = B;
       void* args[] = {&e->X, &e->LAM, &e->FIX, &tm, &wm, &ms.S, &ms.W, &ms.OUT, &Bi, &e->dpool, &e->ipool};
       const long long threads = (long long)B * np_.n_nodes;
-      CK(cudaLaunchKernel((void*)ms.node_kernels[p], dim3(blocks_for(threads, 128)), dim3(128), args, 0, st));
+      cudaStream_t sp = (!spread || p == 0) ? st : (p % 2 == 1 ? ms.aux1 : ms.aux2);
+      CK(cudaLaunchKernel((void*)ms.node_kernels[p], dim3(blocks_for(threads, 128)), dim3(128), args, 0, sp));
       ++e->launches;
+    }
+    if (spread) {
+      CK(cudaEventRecord(ms.node_join[0], ms.aux1));
+      CK(cudaStreamWaitEvent(st, ms.node_join[0], 0));
+      if (ms.node_kernels.size() > 2) {
+        CK(cudaEventRecord(ms.node_join[1], ms.aux2));
+        CK(cudaStreamWaitEvent(st, ms.node_join[1], 0));
+      }
     }
     if (e->stagger) CK(cudaEventRecord(ms.node_done, st));
     tr(e, mode, 6, 1, st);
@@ -1370,7 +1402,7 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
       const char* pe = getenv("POCKIT_B200_GRAPH_PRIORITY");
       int prio_lo = 0, prio_hi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-      if (!(pe && pe[0] == '0') && prio_hi != prio_lo) {
+      if (pe && pe[0] == '1' && prio_hi != prio_lo) {
         size_t n_nodes = 0;
         CK(cudaGraphGetNodes(graph, nullptr, &n_nodes));
         std::vector<cudaGraphNode_t> nodes(n_nodes);
@@ -1393,7 +1425,17 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
         }
       }
     }
-    CK(cudaGraphInstantiate(&e->set_graph, graph, 0));
+    {
+      // the per-node priorities set above only take effect when the executable graph is instantiated with
+      // cudaGraphInstantiateFlagUseNodePriority (round 1 instantiated with flags = 0 and measured "no effect")
+      const char* pe = getenv("POCKIT_B200_GRAPH_PRIORITY");
+      // Opt-in (POCKIT_B200_GRAPH_PRIORITY=1): measured again WITH the flag in round 2
+      // (profiles/r02_call17_graph_priority.log) -- humanoid 122.2 vs 121.5 us, rocket 55.4 vs 55.5, robot_arm
+      // 61.5 vs 58.1, quadrotor batch 271 vs 264: the kernels of a set share bandwidth and issue slots, not a
+      // dispatch queue, so priorities do not help.
+      const unsigned long long flags = (pe && pe[0] == '1') ? (unsigned long long)cudaGraphInstantiateFlagUseNodePriority : 0ull;
+      CK(cudaGraphInstantiateWithFlags(&e->set_graph, graph, flags));
+    }
     cudaGraphDestroy(graph);
     e->set_modes = want;
   }

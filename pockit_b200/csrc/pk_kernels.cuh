@@ -584,6 +584,24 @@ __global__ void __launch_bounds__(PK_THREADS) pk_generic_jobs(PkCtx cx, const pk
     }
     return;
   }
+  if (type == PK_JOB_SCALED && !(jb.flags & PK_F_A_SCALAR)) {  // integral lists x dF/dI [x sigma | lambda_i]: a node-table row scaled
+    const double* __restrict__ w0 = cx.W + jb.i[6] + jb.i[8];
+    const long long lm = jb.i[7];
+    const long long sys_slot = jb.i[3], post_kind = jb.i[4], post_row = jb.i[5];
+#pragma unroll
+    for (int it = 0; it < PK_ITEMS; ++it) {
+      const IT idx = i0 + (IT)it * PK_THREADS;
+      if (idx >= total) break;
+      unsigned b; IT e;
+      pk_split<IT>(idx, count, magic, b, e);
+      const double sysv = sys_slot >= 0 ? cx.S[(long long)b * cx.n_scalar + sys_slot] : 1.0;
+      double v = w0[(long long)b * lm + (long long)e] * sysv;
+      if (post_kind == 1) v = v * cx.SIG[b];
+      if (post_kind == 2) v = v * cx.LAM[(long long)b * cx.m + post_row];
+      pk_store(out0 + (long long)b * cx.n_out + (long long)e, v, cx.stream);
+    }
+    return;
+  }
   for (int it = 0; it < PK_ITEMS; ++it) {
     const IT idx = i0 + (IT)it * PK_THREADS;
     if (idx >= total) break;
