@@ -352,9 +352,9 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
   if (t0 >= J.pairs) return;  // lists of a shorter job
   const unsigned t = t0 + threadIdx.x;
   const bool live = t < J.pairs;
-  const unsigned K = (live ? t : J.pairs - 1) / (unsigned)n;
+  const unsigned K = pk_div(live ? t : J.pairs - 1, prm.m_n);  // / n by the pre-computed reciprocal
   const unsigned cc = (live ? t : J.pairs - 1) - K * (unsigned)n;
-  const unsigned K0 = t0 / (unsigned)n;
+  const unsigned K0 = pk_div(t0, prm.m_n);
   // the two loads the stores depend on go out first
   const double sv = cx.W[L.wbase + (long long)b * J.Lm + J.node0 + (long long)K * J.step + cc];
   const double w = cx.dpool[J.width + K];
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
     if (LAM) {
       unsigned tl = t0 + PK_XC_THREADS - 1;
       if (tl >= J.pairs) tl = J.pairs - 1;
-      const int n_lam = (int)(tl / (unsigned)n - K0 + 1) * rows;
+      const int n_lam = (int)(pk_div(tl, prm.m_n) - K0 + 1) * rows;
       const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K0 * rows;
       for (int q = threadIdx.x; q < n_lam; q += PK_XC_THREADS) lam_s[q] = lam[q];
     }
@@ -464,13 +464,13 @@ __global__ void __launch_bounds__(PK_XB_THREADS) pk_expand_bulk(PkCtx cx, const 
   const PkXcList& L = prm.list[blockIdx.y];
   const PkXcJob& J = prm.job[L.job];
   const int b = blockIdx.z;
-  const unsigned nK = J.pairs / (unsigned)n;
+  const unsigned nK = pk_div(J.pairs, prm.m_n);
   const unsigned K0 = blockIdx.x * (unsigned)per_block;
   if (K0 >= nK) return;  // lists of a shorter job
   const unsigned Kn = nK - K0 < (unsigned)per_block ? nK - K0 : (unsigned)per_block;  // intervals of this block
   const unsigned t = threadIdx.x;
   const bool live = t < Kn * (unsigned)n;
-  const unsigned kk = live ? t / (unsigned)n : 0;
+  const unsigned kk = live ? pk_div(t, prm.m_n) : 0;
   const unsigned cc = live ? t - kk * (unsigned)n : 0;
   const unsigned K = K0 + kk;
   double sv = 0.0, w = 0.0;
