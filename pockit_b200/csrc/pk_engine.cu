@@ -1173,10 +1173,10 @@ static int eval_set(pk_engine* e, const double* x, const double* lam, const doub
     for (size_t q = 0; q < e->pending.size(); ++q)
       if (e->pending[q] == modes[k]) { e->pending.erase(e->pending.begin() + q); break; }
   if (x && pk_upload_x(e, x)) return 1;
-  if (hess && pk_upload_multipliers(e, lam, sig)) return 1;
   unsigned asked = 0;
   for (int k = 0; k < n_modes; ++k) asked |= 1u << modes[k];
   if (use_pipeline(e, modes, n_modes) == asked) {
+    if (hess && pk_upload_multipliers(e, lam, sig)) return 1;
     // one pipeline for everything that was asked for; the copies of its slices follow on the same stream, largest first
     CK(cudaEventRecord(e->fork, e->stream));
     ModeState& ps = e->mode[PK_MODE_SET];
@@ -1205,15 +1205,28 @@ static int eval_set(pk_engine* e, const double* x, const double* lam, const doub
     for (int b = a; b > 0 && e->mode[modes[order[b]]].n_out > e->mode[modes[order[b - 1]]].n_out; --b) {
       const int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t;
     }
-  for (int q = 0; q < n_modes; ++q) {
-    const int k = order[q];
-    ModeState& ms = e->mode[modes[k]];
-    CK(cudaStreamWaitEvent(ms.stream, e->fork, 0));
-    if (launch_mode(e, modes[k], ~0u, ms.stream)) return 1;
-    if (download_async(e, modes[k], outs[k], ms.stream)) return 1;
-    CK(cudaEventRecord(ms.done, ms.stream));
+  // Two passes: everything that does not read the multipliers starts right behind the upload of x -- the
+  // Jacobian is expanded and its copy is on the link while the host still stages the multipliers; the
+  // Hessian follows their upload.  The engine stream is joined to the modes only at the very end, so the
+  // upload in between does not wait for the first pass (device-to-host copies included).
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      if (hess && pk_upload_multipliers(e, lam, sig)) return 1;
+      CK(cudaEventRecord(e->fork, e->stream));
+    }
+    for (int q = 0; q < n_modes; ++q) {
+      const int k = order[q];
+      if ((modes[k] == PK_MODE_HESSIAN || modes[k] == PK_MODE_SET) != (pass == 1)) continue;
+      ModeState& ms = e->mode[modes[k]];
+      CK(cudaStreamWaitEvent(ms.stream, e->fork, 0));
+      if (launch_mode(e, modes[k], ~0u, ms.stream)) return 1;
+      if (download_async(e, modes[k], outs[k], ms.stream)) return 1;
+      CK(cudaEventRecord(ms.done, ms.stream));
+    }
+  }
+  for (int k = 0; k < n_modes; ++k) {
     if (wait)
-      CK(cudaStreamWaitEvent(e->stream, ms.done, 0));
+      CK(cudaStreamWaitEvent(e->stream, e->mode[modes[k]].done, 0));
     else
       e->pending.push_back(modes[k]);  // the engine stream stays free for the next stage's uploads
   }
