@@ -822,16 +822,28 @@ static int launch_mode(pk_engine* e, int mode, unsigned stage_mask, cudaStream_t
       ++e->launches;
     }
     if (ms.def_fast) {
-      for (size_t j = 0; j < ms.def_geo.size(); ++j) {
-        const ModeState::DefectGeo& dg = ms.def_geo[j];
-        if (!dg.fast) continue;
-        const long long total = dg.rows * dg.n_x * (long long)B;
-        const PkDefectDiv dv = {div_multiplier((unsigned long long)dg.rows), div_multiplier((unsigned long long)dg.n_x),
-                                div_multiplier((unsigned long long)dg.rb)};
-        if (total < (1LL << 32))
-          pk_defects_blocks<true><<<blocks_for(total, PK_THREADS), PK_THREADS, 0, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)j, B, dv);
+      // all phases' defect jobs in one launch (blockIdx.y), PK_DEF_JOBS at a time
+      for (size_t j0 = 0; j0 < ms.def_geo.size(); j0 += PK_DEF_JOBS) {
+        const size_t nj = ms.def_geo.size() - j0 < PK_DEF_JOBS ? ms.def_geo.size() - j0 : PK_DEF_JOBS;
+        PkDefectDivs dvs;
+        memset(&dvs, 0, sizeof(dvs));
+        long long most = 0;
+        bool any = false;
+        for (size_t j = 0; j < nj; ++j) {
+          const ModeState::DefectGeo& dg = ms.def_geo[j0 + j];
+          if (!dg.fast) continue;
+          any = true;
+          dvs.d[j] = {div_multiplier((unsigned long long)dg.rows), div_multiplier((unsigned long long)dg.n_x),
+                      div_multiplier((unsigned long long)dg.rb)};
+          const long long total = dg.rows * dg.n_x * (long long)B;
+          if (total > most) most = total;
+        }
+        if (!any) continue;
+        const dim3 dgrid(blocks_for(most, PK_THREADS), (unsigned)nj);
+        if (most < (1LL << 32))
+          pk_defects_blocks<true><<<dgrid, PK_THREADS, 0, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)j0, B, dvs);
         else
-          pk_defects_blocks<false><<<blocks_for(total, PK_THREADS), PK_THREADS, 0, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)j, B, dv);
+          pk_defects_blocks<false><<<dgrid, PK_THREADS, 0, a1>>>(cx, ms.jobs[PK_STAGE_DEFECT], (int)j0, B, dvs);
         ++e->launches;
       }
     }

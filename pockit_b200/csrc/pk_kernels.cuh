@@ -198,10 +198,17 @@ __global__ void __launch_bounds__(PK_THREADS) pk_defects(PkCtx cx, const pk_job*
 struct PkDefectDiv {
   unsigned long long rows, n_x, rb;  // division multipliers (pk_div)
 };
+#define PK_DEF_JOBS 8
+struct PkDefectDivs {
+  PkDefectDiv d[PK_DEF_JOBS];  // one per defect job (= phase) of the launch: blockIdx.y
+};
 
 template <bool FAST>
-__global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const pk_job* __restrict__ jobs, int job, int B, PkDefectDiv dv) {
-  const pk_job& jb = jobs[job];
+__global__ void __launch_bounds__(PK_THREADS) pk_defects_blocks(PkCtx cx, const pk_job* __restrict__ jobs, int job0, int B,
+                                                               const __grid_constant__ PkDefectDivs dvs) {
+  const pk_job& jb = jobs[job0 + blockIdx.y];
+  if (!jb.i[13]) return;  // a table-driven job (mixed orders): pk_defects
+  const PkDefectDiv& dv = dvs.d[blockIdx.y];
   const int n = (int)jb.i[13];
   const unsigned rb = (unsigned)jb.flags;
   const unsigned rows = (unsigned)jb.i[4], n_x = (unsigned)jb.i[3];

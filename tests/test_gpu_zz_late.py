@@ -82,6 +82,30 @@ def test_mesh_shards_on_one_device_reassemble(G):
     assert np.array_equal(jac, want_j) and np.array_equal(hess, want_h)
 
 
+def test_weighted_mesh_shards_on_one_device_reassemble():
+    """shard = (rank, world, weights): shares sized by the ranks' link rates (meshshard measures them) still
+    partition the output; an LGL mesh, so every shard runs the TMA bulk-store expansion."""
+    import pockit_b200.lobatto as lob
+    from pockit_b200 import plan as P
+    from pockit_b200 import problems
+    from pockit_b200.engine import Engine
+
+    S = problems.rocket(lob, mesh=300, num_point=10)
+    x, lam, sigma = problems.evaluation_point(S, seed=4)
+    want_j, want_h = S.jacobian(x), S.hessian(x, lam, sigma)
+    jac, hess = np.full(len(want_j), np.nan), np.full(len(want_h), np.nan)
+    w = [13.0, 12.9, 22.5, 25.0]
+    owned = []
+    for g in range(4):
+        eng = Engine(S.lowering, shard=(g, 4, w))
+        assert eng.expand_kernel(P.JAC) in ("pk_expand_bulk", "pk_expand_blocks")
+        eng.evaluate(x, lam, sigma, modes=[P.JAC, P.HESS], outs=[jac, hess])
+        owned.append(int(eng.fin[P.JAC]["runs"][:, 1].sum()))
+        eng.close()
+    assert sum(owned) == len(want_j) and owned[3] > owned[0]
+    assert np.array_equal(jac, want_j) and np.array_equal(hess, want_h)
+
+
 def _mesh_rank(rank, world, port, q):
     import os
     import sys
