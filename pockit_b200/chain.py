@@ -21,7 +21,7 @@ order included, while the values become straight-line device code.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Optional, Sequence, Union
+from typing import Sequence, Union
 
 __all__ = ["Leaf", "Prod", "Term", "ONE", "GEntry", "HEntry", "Sym", "compose", "precedes"]
 

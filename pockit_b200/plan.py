@@ -27,8 +27,8 @@ from typing import Optional
 import numpy as np
 import sympy as sp
 
-from .chain import Leaf, Prod, Term
-from .emit import PRELUDE, CExpr, emit_block
+from .chain import Leaf, Term
+from .emit import PRELUDE, emit_block
 from .phase import BcType, Segment
 from .system import SysList, SysSegment, SystemLowering
 

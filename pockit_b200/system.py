@@ -13,14 +13,14 @@ hand ``x`` (and multipliers) to the CUDA engine through the C-ABI in
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Iterable, Optional
 
 import numpy as np
 import sympy as sp
 
-from .chain import ONE, GEntry, HEntry, Sym, Term, compose, leaf
-from .phase import BcType, Phase, PhaseLowering, Segment
+from .chain import GEntry, HEntry, Term, leaf
+from .phase import BcType, Phase, Segment
 from .symfunc import SymFunc
 
 __all__ = ["System", "SysSegment", "SystemLowering", "continuous_error_intervals"]

@@ -7,7 +7,7 @@ against the oracle.
     compute-sanitizer --tool memcheck  --error-exitcode 9 python tools/sanitize_target.py
     compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_target.py
 """
-import os, sys, importlib
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
