@@ -163,6 +163,56 @@ def test_ipopt_adapter_needs_cyipopt():
         ipopt.solve(problems.lqr(lob, 3, 3), None)
 
 
+def test_ipopt_adapter_wiring_with_a_stand_in_for_cyipopt(monkeypatch):
+    """cyipopt / libipopt are not in this image, so Ipopt itself cannot run; the adapter's own code can: a
+    stand-in module with cyipopt's interface (``Problem(n, m, problem_obj, lb, ub, cl, cu)``,
+    ``add_option``, ``solve(x0) -> (x, info)``) drives the callbacks in Ipopt's order and with Ipopt's
+    argument convention ``hessian(x, lagrange, obj_factor)`` (``pockit/optimizer/ipopt.py:41-53``), on the
+    host-emulated plan.  Checks sizes, structures, the x-keyed cache and the returned solution layout."""
+    import sys
+    import types
+
+    S, g = build("robot_arm_lgr_6x20"), load("robot_arm_lgr_6x20")
+    F = FakeSystem(S)
+    seen = {}
+
+    class Problem:
+        def __init__(self, n, m, problem_obj, lb, ub, cl, cu):
+            assert n == S.L and m == len(S.c_lb) and len(lb) == len(ub) == n and len(cl) == len(cu) == m
+            self.n, self.m, self.obj, self.options = n, m, problem_obj, {}
+
+        def add_option(self, k, v):
+            self.options[k] = v
+
+        def solve(self, x0):
+            o = self.obj
+            jr, jc = o.jacobianstructure()
+            hr, hc = o.hessianstructure()
+            x = np.array(g["x"], copy=True)  # evaluate at the golden point, as one Ipopt iteration would
+            seen["f"], seen["grad"], seen["c"] = o.objective(x), o.gradient(x), o.constraints(x)
+            seen["jac"] = o.jacobian(x)
+            seen["hess"] = o.hessian(x, g["lam"], float(g["sigma"]))  # (x, lagrange, obj_factor)
+            assert len(seen["jac"]) == len(jr) == len(jc) and len(seen["hess"]) == len(hr) == len(hc)
+            return x0, {"status": 0, "obj_val": float(seen["f"]), "options": dict(self.options)}
+
+    monkeypatch.setitem(sys.modules, "cyipopt", types.SimpleNamespace(Problem=Problem))
+    from pockit_b200.guess import Variable
+    from pockit_b200.optimizer import ipopt
+
+    x0 = g["x"]
+    guess = Variable(S.p[0], x0[S.l_p[0] : S.r_p[0]].copy())
+    result, info = ipopt.solve(F, guess, {"max_iter": 7, "tol": 1e-9})
+    assert info["options"] == {"max_iter": 7, "tol": 1e-9} and info["status"] == 0
+    np.testing.assert_allclose(seen["f"], g["objective"], rtol=1e-12)
+    np.testing.assert_allclose(seen["grad"], g["gradient"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(seen["c"], g["constraints"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(seen["jac"], g["jacobian"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(seen["hess"], g["hessian"], rtol=1e-12, atol=1e-14)
+    # five callbacks at one point: x sent once, three engine calls ({f, g}, {grad f, J}, H)
+    assert info["cache_stats"] == {"points": 1, "engine_calls": 3, "hits": 2}
+    assert isinstance(result, Variable) and len(result.data) == S.p[0].L
+
+
 def test_scipy_adapter_solves_the_lqr_like_the_reference_on_the_host_emulated_plan():
     """Solver-level parity without a GPU: pockit_b200.optimizer.scipy.solve wired to the
     host-emulated plan must walk the reference's own trust-constr path on the LQR
