@@ -366,13 +366,17 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
   const double sv = cx.W[L.wbase + (long long)b * J.Lm + J.node0 + (long long)K * J.step + cc];
   const double w = cx.dpool[J.width + K];
   {
+    // short trip counts (1-4): keep the staging loops rolled -- unrolled, their set-up code alone was a third of
+    // the instructions a thread executes (ncu source page of the bulk variant, round 2)
     const double* unit = cx.dpool + prm.unit;
+#pragma unroll 1
     for (int q = threadIdx.x; q < bn; q += PK_XC_THREADS) u_s[q] = prm.sign * unit[q];
     if (LAM) {
       unsigned tl = t0 + PK_XC_THREADS - 1;
       if (tl >= J.pairs) tl = J.pairs - 1;
       const int n_lam = (int)(pk_div(tl, prm.m_n) - K0 + 1) * rows;
       const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K0 * rows;
+#pragma unroll 1
       for (int q = threadIdx.x; q < n_lam; q += PK_XC_THREADS) lam_s[q] = lam[q];
     }
   }
@@ -487,9 +491,11 @@ __global__ void __launch_bounds__(PK_XB_THREADS) pk_expand_bulk(PkCtx cx, const 
   }
   {
     const double* unit = cx.dpool + prm.unit;
+#pragma unroll 1
     for (int q = t; q < bn; q += PK_XB_THREADS) u_s[q] = prm.sign * unit[q];
     if (LAM) {
       const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K0 * rows;
+#pragma unroll 1
       for (int q = t; q < (int)Kn * rows; q += PK_XB_THREADS) lam_s[q] = lam[q];
     }
   }
