@@ -454,8 +454,11 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bulk-store variant of the parameter-driven column walk (opt-in, POCKIT_B200_EXPAND=bulk; written
-// after the round-1 GPU budget was spent, so it is compiled and SASS-checked but NOT yet run).
+// Bulk-store variant of the parameter-driven column walk: the default for interval blocks that are not a
+// whole number of 32-byte sectors (LGL n = 10: 9 x 10 = 90 slots), where it is 10-15 % faster than the
+// column walk's 8-byte stores (humanoid set 128.7 -> 121.4 us); slower on sector-aligned 20 x 20 blocks,
+// where the column walk stays (POCKIT_B200_EXPAND=bulk | params overrides).  Bit-identical to the other
+// kernels (tests/test_gpu_baseline_sizes.py), memcheck / racecheck clean.
 // A block owns PK_XB_PAIRS / n WHOLE intervals of one list, i.e. one contiguous run of output slots.
 // Its threads compute the same values with the same association as pk_expand_cols, but store them
 // into a shared-memory image of that run; one thread then hands the image to the TMA engine as a

@@ -651,9 +651,10 @@ class DevicePlan:
                 self.shard_cum = [float(v) for v in c]
             shard = (g, G)
         self.shard = shard
-        # node_groups > 1: up to that many threads per node, one per group of functions (measured
-        # default pending: it shortens the latency-bound per-node programs at the price of
-        # re-evaluating subexpressions the functions share)
+        # node_groups > 1: up to that many threads per node, one per group of functions.  Measured on B200
+        # (round 2): slower -- robot_arm set 59.8 -> 60.0 / 61.4 us with 2 / 4 groups, humanoid 143.7 ->
+        # 159.9 / 164.6: re-evaluating the subexpressions the functions share costs more than the shorter
+        # per-thread chains save.  Kept as an opt-in switch (POCKIT_B200_NODE_GROUPS).
         self.node_groups = max(1, int(node_groups))
         # fused=True: the per-node program itself walks its block column and writes the slots (no
         # node-table round trip, one launch less).  Measured on B200 (round 1) it is SLOWER than the

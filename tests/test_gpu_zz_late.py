@@ -1,7 +1,6 @@
-"""GPU tests written after the round's GPU budget was spent: they exercise code whose pieces were
-verified separately (host-emulated programs on the CPU tier, the engine paths by the earlier GPU
-tests) but could not be run on a B200 themselves this round.  The file sorts last on purpose, so a
-surprise here cannot hide the rest of the suite behind ``pytest -x``."""
+"""GPU tests of the outer layers -- continuous error check, cubin cache, mesh sharding (single device and
+two processes) -- that sort last on purpose: a surprise here cannot hide the parity tests behind
+``pytest -x``.  (Written late in round 1; all of them have run on B200s since.)"""
 import numpy as np
 import pytest
 
