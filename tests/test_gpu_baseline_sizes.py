@@ -10,9 +10,9 @@ those the oracle was pinned on).
 The block expansion (``phasebase.py:1120-1124, 1280-1285``) has four kernels (the fourth,
 pk_expand_batch, is exercised by the batched test); every test asserts
 that the engine really launches the one it claims to test (``Engine.expand_kernel``):
-``columns`` -> pk_expand_blocks (persistent), ``params`` -> pk_expand_cols (the default at these
-sizes, the kernel the bench and the roofline figure run on), ``bulk`` -> pk_expand_bulk (TMA
-bulk stores).
+``columns`` -> pk_expand_blocks (persistent), ``params`` -> pk_expand_cols (the default where a
+block is a whole number of 32-byte sectors: C2, the kernel the bench and the roofline figure run
+on), ``bulk`` -> pk_expand_bulk (TMA bulk stores; the default for the 9 x 10 blocks of C3 / C4).
 """
 import importlib
 
