@@ -55,7 +55,8 @@ struct ExpandGroup {
   // bulk-store variant of it (opt-in): whole intervals per block, image handed to the TMA engine
   bool bulk = false; int xb_per_block = 0; unsigned xb_gx = 0; size_t xb_smem = 0;
   // batches of small problems: parameter-driven, (instance, pair) space flattened over the grid
-  bool batch = false; unsigned xbt_gx = 0;
+  bool batch = false; unsigned xbt_gx = 0; int batch_lists = PK_XM_LISTS, batch_rows = PK_XM_ROWS; size_t batch_smem = 0;
+  bool slots = false; unsigned xsl_gx = 0; int slot_lists = 2;  // pk_expand_slots (a batch variant)
 };
 
 struct ModeState {
@@ -421,6 +422,15 @@ static int build_block_map(const pk_job* jobs, long long n, int field, int per, 
   return 0;
 }
 
+// pk_expand_batch is instantiated for a few unrolled row counts; the smallest one that holds the block rows
+typedef void (*BatchKernel)(PkCtx, const PkXcParams, unsigned, int);
+static BatchKernel batch_kernel(bool lam, int rows) {
+#define PK_BK(R) if (rows <= R) return lam ? pk_expand_batch<true, R> : pk_expand_batch<false, R>;
+  PK_BK(4) PK_BK(5) PK_BK(6) PK_BK(8) PK_BK(10) PK_BK(12)
+#undef PK_BK
+  return lam ? pk_expand_batch<true, PK_XM_ROWS> : pk_expand_batch<false, PK_XM_ROWS>;
+}
+
 static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, long long count, ExpandGroup& g) {
   g.first = first;
   g.count = count;
@@ -456,6 +466,8 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
   if (const char* env = getenv("POCKIT_B200_EXPAND")) {
     if (!strcmp(env, "params") && !cols) return fail("POCKIT_B200_EXPAND=params: jobs do not fit the parameter-driven kernel");
     if (!strcmp(env, "batch") && !batch) return fail("POCKIT_B200_EXPAND=batch: jobs do not fit the batch kernel");
+    if (!strcmp(env, "slots") && !(batch && max_pairs * r0 * e->dims.batch < (1LL << 32)))
+      return fail("POCKIT_B200_EXPAND=slots: jobs do not fit the slot-order batch kernel");
     if (!strcmp(env, "columns")) cols = batch = false;
     if (!strcmp(env, "bulk") && !cols) return fail("POCKIT_B200_EXPAND=bulk: jobs do not fit the parameter-driven kernel");
   }
@@ -463,17 +475,44 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
     g.cols = cols;
     g.batch = batch;
     g.xbt_gx = (unsigned)((max_pairs * e->dims.batch + PK_XC_THREADS - 1) / PK_XC_THREADS);
+    if (batch) {
+      // slot-order variant (a thread per output slot, warps write consecutive doubles): POCKIT_B200_EXPAND=slots
+      const char* env = getenv("POCKIT_B200_EXPAND");
+      g.slots = env && !strcmp(env, "slots");
+      g.xsl_gx = (unsigned)((max_pairs * r0 * e->dims.batch + PK_XC_THREADS - 1) / PK_XC_THREADS);
+      // experiment knobs: unrolled row count (exact = smallest instantiation that holds the rows; default 16) and
+      // an unused dynamic shared-memory request that caps the resident blocks per SM
+      if (const char* pr = getenv("POCKIT_B200_BATCH_ROWS"))
+        if (!strcmp(pr, "exact")) g.batch_rows = (int)r0;
+      if (const char* psm = getenv("POCKIT_B200_BATCH_SMEM")) {
+        const long long v = atoll(psm);
+        if (v > 0 && v <= 200 * 1024) {
+          g.batch_smem = (size_t)v;
+          if (v > 48 * 1024) CK(cudaFuncSetAttribute((const void*)batch_kernel(g.lam, g.batch_rows), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v));
+        }
+      }
+      if (const char* pl = getenv("POCKIT_B200_BATCH_LISTS")) {
+        const int v = atoi(pl);
+        if (v >= 1 && v <= PK_XC_LISTS) g.batch_lists = v;
+      }
+      if (const char* pl = getenv("POCKIT_B200_SLOT_LISTS")) {
+        const int v = atoi(pl);
+        if (v >= 1 && v <= PK_XC_LISTS) g.slot_lists = v;
+      }
+    }
     g.xc_smem = xsm;
     PkXcParams& q = g.xc;
     memset(&q, 0, sizeof(q));
     q.n = (int)n0; q.rows = (int)r0; q.n_jobs = (int)count; q.unit = ej[0].i[7]; q.sign = ej[0].f[0];
     q.m_n = div_multiplier((unsigned long long)n0);
+    q.m_bn = div_multiplier((unsigned long long)(n0 * r0));
     int li = 0;
     for (int j = 0; j < q.n_jobs; ++j) {
       const pk_job& jb = ej[j];
       q.job[j].lam0 = jb.i[2]; q.job[j].node0 = jb.i[6]; q.job[j].width = jb.i[8]; q.job[j].Lm = jb.i[10];
       q.job[j].step = (int)jb.i[5]; q.job[j].pairs = (unsigned)jb.i[11];
       q.job[j].m_pairs = div_multiplier((unsigned long long)jb.i[11]);
+      q.job[j].m_run = div_multiplier((unsigned long long)(jb.i[11] * r0));
       q.job[j].list0 = li; q.job[j].n_lists = (int)jb.i[1];
       for (long long l = 0; l < jb.i[1]; ++l, ++li) {
         const size_t at = (size_t)(jb.i[0] + 2 * l);
@@ -710,14 +749,19 @@ static void launch_expand(const ModeState& ms, const PkCtx& cx, int B, cudaStrea
         pk_expand_bulk<true><<<grid, PK_XB_THREADS, g.xb_smem, st>>>(cx, g.xc, g.xb_per_block);
       else
         pk_expand_bulk<false><<<grid, PK_XB_THREADS, g.xb_smem, st>>>(cx, g.xc, g.xb_per_block);
+    } else if (g.batch && g.slots) {
+      unsigned groups = 0;
+      for (int j = 0; j < g.xc.n_jobs; ++j) groups += (unsigned)((g.xc.job[j].n_lists + g.slot_lists - 1) / g.slot_lists);
+      const dim3 grid(g.xsl_gx, groups);
+      if (g.lam)
+        pk_expand_slots<true><<<grid, PK_XC_THREADS, g.batch_smem <= 48 * 1024 ? g.batch_smem : 0, st>>>(cx, g.xc, (unsigned)B, g.slot_lists);
+      else
+        pk_expand_slots<false><<<grid, PK_XC_THREADS, g.batch_smem <= 48 * 1024 ? g.batch_smem : 0, st>>>(cx, g.xc, (unsigned)B, g.slot_lists);
     } else if (g.batch) {
       unsigned groups = 0;
-      for (int j = 0; j < g.xc.n_jobs; ++j) groups += (unsigned)((g.xc.job[j].n_lists + PK_XM_LISTS - 1) / PK_XM_LISTS);
+      for (int j = 0; j < g.xc.n_jobs; ++j) groups += (unsigned)((g.xc.job[j].n_lists + g.batch_lists - 1) / g.batch_lists);
       const dim3 grid(g.xbt_gx, groups);
-      if (g.lam)
-        pk_expand_batch<true><<<grid, PK_XC_THREADS, 0, st>>>(cx, g.xc, (unsigned)B);
-      else
-        pk_expand_batch<false><<<grid, PK_XC_THREADS, 0, st>>>(cx, g.xc, (unsigned)B);
+      batch_kernel(g.lam, g.batch_rows)<<<grid, PK_XC_THREADS, g.batch_smem, st>>>(cx, g.xc, (unsigned)B, g.batch_lists);
     } else if (g.cols) {
       const dim3 grid(g.xc_gx, (unsigned)g.xc.n_lists, B);
       if (g.lam)
@@ -1433,16 +1477,19 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
         std::vector<cudaGraphNode_t> nodes(n_nodes);
         if (n_nodes) CK(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
         const void* big[] = {(const void*)pk_expand_cols<true>, (const void*)pk_expand_cols<false>, (const void*)pk_expand_blocks,
-                             (const void*)pk_expand_batch<true>, (const void*)pk_expand_batch<false>};
+                             (const void*)pk_expand_slots<true>, (const void*)pk_expand_slots<false>};
         for (cudaGraphNode_t nd : nodes) {
           cudaGraphNodeType ty;
           if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
           cudaKernelNodeParams kp;
           bool is_big = false;
-          if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess)
+          if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess) {
             for (const void* f : big) is_big = is_big || kp.func == f;
-          else
+            for (int rr = 1; rr <= PK_XM_ROWS && !is_big; ++rr)
+              is_big = kp.func == (const void*)batch_kernel(true, rr) || kp.func == (const void*)batch_kernel(false, rr);
+          } else {
             (void)cudaGetLastError();  // library (NVRTC) kernels: not a host function pointer -- small by construction
+          }
           cudaLaunchAttributeValue v;
           memset(&v, 0, sizeof(v));
           v.priority = is_big ? prio_lo : prio_hi;
@@ -1645,7 +1692,7 @@ extern "C" int pk_x_uploads(pk_engine* e, int64_t* count) {
 extern "C" int pk_expand_variant(pk_engine* e, int mode, int* variant) {
   if (!e || !variant || mode < 0 || mode >= PK_N_MODES) return fail("pk_expand_variant: bad argument");
   const ModeState& ms = e->mode[mode];
-  *variant = ms.exp.empty() ? 0 : (ms.exp.back().bulk ? 3 : (ms.exp.back().cols ? 2 : (ms.exp.back().batch ? 4 : 1)));
+  *variant = ms.exp.empty() ? 0 : (ms.exp.back().bulk ? 3 : (ms.exp.back().cols ? 2 : (ms.exp.back().batch ? (ms.exp.back().slots ? 5 : 4) : 1)));
   return 0;
 }
 

@@ -330,6 +330,7 @@ struct PkXcJob {
   int step;          // nodes per interval step
   unsigned pairs;    // intervals * n
   unsigned long long m_pairs;  // division multiplier of pairs (pk_div)
+  unsigned long long m_run;    // division multiplier of pairs * rows (slots of one list of one instance)
   int list0, n_lists;          // the job's lists are prm.list[list0 .. list0 + n_lists)
 };
 struct PkXcList {
@@ -341,6 +342,7 @@ struct PkXcParams {
   long long unit;  // dpool offset of the unit block
   double sign;
   unsigned long long m_n;  // division multiplier of n
+  unsigned long long m_bn; // division multiplier of n * rows
   PkXcJob job[PK_XC_JOBS];
   PkXcList list[PK_XC_LISTS];
 };
@@ -408,21 +410,29 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
 // and found it slower there: that case is bound by the store streams, this one by instruction issue.)
 #define PK_XM_ROWS 16
 #define PK_XM_LISTS 2  // lists per thread
-template <bool LAM>
-__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B) {
+// ROWS >= rows is the unrolled trip count of the row loops.  The default launch uses ROWS = 16 for every
+// block shape: the exact instantiation (POCKIT_B200_BATCH_ROWS=exact) executes a third of the instructions
+// for 5-row blocks and needs 32 registers instead of 48, and is SLOWER on configs[4] (Jacobian expansion
+// 68 -> 83 us, set 262 -> 273 us): the kernel is bound by how the memory system takes ~3 KB output runs
+// 34 KB apart, 16 resident blocks per SM push more of them at once than 10 do.  Capping the resident blocks
+// further (POCKIT_B200_BATCH_SMEM) is slower again (8 per SM: 276 us, 4: 326 us) -- profiles/
+// r02_call26_batch_rows_exact.log, r02_call27_batch_occupancy_cap.log.
+template <bool LAM, int ROWS>
+__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B,
+                                                                  int per_thread) {
   const int n = prm.n, rows = prm.rows;
   const int bn = n * rows;
-  // blockIdx.y enumerates (job, group of PK_XM_LISTS lists): a thread writes at most PK_XM_LISTS columns, so
+  // blockIdx.y enumerates (job, group of per_thread lists; PK_XM_LISTS unless overridden): a thread writes at most that many columns, so
   // that jobs with many lists still spread over enough threads (8 lists per thread: 590 k threads for the
   // quadrotor Jacobian, 80 us; 2 per thread as in its Hessian: 32 us for half the bytes)
   int jj = 0, grp = (int)blockIdx.y;
-  while (grp >= (prm.job[jj].n_lists + PK_XM_LISTS - 1) / PK_XM_LISTS) {
-    grp -= (prm.job[jj].n_lists + PK_XM_LISTS - 1) / PK_XM_LISTS;
+  while (grp >= (prm.job[jj].n_lists + per_thread - 1) / per_thread) {
+    grp -= (prm.job[jj].n_lists + per_thread - 1) / per_thread;
     ++jj;
   }
   const PkXcJob& J = prm.job[jj];
-  const int l_lo = J.list0 + grp * PK_XM_LISTS;
-  const int l_hi = l_lo + PK_XM_LISTS < J.list0 + J.n_lists ? l_lo + PK_XM_LISTS : J.list0 + J.n_lists;
+  const int l_lo = J.list0 + grp * per_thread;
+  const int l_hi = l_lo + per_thread < J.list0 + J.n_lists ? l_lo + per_thread : J.list0 + J.n_lists;
   const unsigned t = blockIdx.x * PK_XC_THREADS + threadIdx.x;  // B * pairs < 2^32 (checked at set-up)
   if (t >= J.pairs * B) return;
   const unsigned b = pk_div(t, J.m_pairs);
@@ -432,9 +442,9 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const
   const double w = cx.dpool[J.width + K];
   const double* __restrict__ u = cx.dpool + prm.unit + cc;
   const double* __restrict__ lam = cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K * rows;
-  double P[PK_XM_ROWS];
+  double P[ROWS];
 #pragma unroll
-  for (int r = 0; r < PK_XM_ROWS; ++r) {
+  for (int r = 0; r < ROWS; ++r) {
     if (r < rows) {
       double v = ((prm.sign * __ldg(u + r * n)) * w) / 2.0;
       if (LAM) v = v * __ldg(lam + r);
@@ -448,8 +458,53 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const
     const double sv = cx.W[L.wbase + wofs];
     double* __restrict__ out = out_b + L.dst;
 #pragma unroll
-    for (int r = 0; r < PK_XM_ROWS; ++r)
+    for (int r = 0; r < ROWS; ++r)
       if (r < rows) pk_store(out + r * n, P[r] * sv, cx.stream);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slot-order variant of the batch expansion.  pk_expand_batch gives a thread a block COLUMN: with
+// 5 x 6 blocks a warp's store instruction then writes 48-byte pieces 240 bytes apart, every one of them a
+// partial 32-byte sector (ncu, round 2: 2.15 sector writes per sector of output, 41 MB of DRAM reads that
+// are fills of partially written sectors, 48 instructions per store instruction because the column set-up
+// is amortised over 10 stores only).  Here a thread owns one SLOT (instance, interval, row, column) of a
+// job -- the slots of one list of one instance are contiguous in the output, so a warp writes 32
+// consecutive doubles per list: whole sectors but for the two ends.  The factor
+// ((sign * unit[r][c]) * width) / 2 [* lambda_r] is formed once per thread and multiplies the list value
+// of each of the thread's lists: same association as every other expansion kernel, bit-identical
+// (tests/test_gpu_baseline_sizes.py).  Measured on B200 it is SLOWER than the column mapping (Jacobian
+// expansion 68 -> 77 us, set 263 -> 280-295 us, profiles/r02_call25_slot_order_batch.log): partial sectors
+// are not what bounds this case.  Opt-in only (POCKIT_B200_EXPAND=slots, POCKIT_B200_SLOT_LISTS).
+template <bool LAM>
+__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_slots(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B,
+                                                                  int per_thread) {
+  const unsigned n = (unsigned)prm.n, rows = (unsigned)prm.rows;
+  const unsigned bn = n * rows;
+  int jj = 0, grp = (int)blockIdx.y;  // (job, group of per_thread lists)
+  while (grp >= (prm.job[jj].n_lists + per_thread - 1) / per_thread) {
+    grp -= (prm.job[jj].n_lists + per_thread - 1) / per_thread;
+    ++jj;
+  }
+  const PkXcJob& J = prm.job[jj];
+  const int l_lo = J.list0 + grp * per_thread;
+  const int l_hi = l_lo + per_thread < J.list0 + J.n_lists ? l_lo + per_thread : J.list0 + J.n_lists;
+  const unsigned run = J.pairs * rows;
+  const unsigned t = blockIdx.x * PK_XC_THREADS + threadIdx.x;  // B * run < 2^32 (checked at set-up)
+  if (t >= run * B) return;
+  const unsigned b = pk_div(t, J.m_run);
+  const unsigned s = t - b * run;
+  const unsigned K = pk_div(s, prm.m_bn);
+  const unsigned q = s - K * bn;  // r * n + c
+  const unsigned r = pk_div(q, prm.m_n);
+  const unsigned cc = q - r * n;
+  const double* __restrict__ wp = cx.W + ((long long)b * J.Lm + J.node0 + (long long)K * J.step + cc);
+  double v = ((prm.sign * __ldg(cx.dpool + prm.unit + q)) * cx.dpool[J.width + K]) / 2.0;
+  if (LAM) v = v * __ldg(cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K * rows + r);
+  double* __restrict__ out_b = cx.OUT + (long long)b * cx.n_out + s;
+  for (int li = l_lo; li < l_hi; ++li) {
+    const PkXcList& L = prm.list[li];
+    pk_store(out_b + L.dst, v * wp[L.wbase], cx.stream);
   }
 }
 

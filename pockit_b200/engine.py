@@ -646,7 +646,7 @@ class Engine:
         self.load(mode)
         v = C.c_int()
         self._check(self.lib.pk_expand_variant(self._h, mode, C.byref(v)))
-        return {0: "", 1: "pk_expand_blocks", 2: "pk_expand_cols", 3: "pk_expand_bulk", 4: "pk_expand_batch"}[v.value]
+        return {0: "", 1: "pk_expand_blocks", 2: "pk_expand_cols", 3: "pk_expand_bulk", 4: "pk_expand_batch", 5: "pk_expand_slots"}[v.value]
 
     def flush_l2(self):
         self._check(self.lib.pk_flush_l2(self._h))

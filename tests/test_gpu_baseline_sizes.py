@@ -149,6 +149,17 @@ def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath, monkeypatc
         assert np.array_equal(bs.jacobian(X), jac) and np.array_equal(bs.hessian(X, LAM, sig), hess)
     finally:
         bs.close()
+    # the slot-order variant (a thread per output slot), with one and with several lists per thread
+    monkeypatch.setenv("POCKIT_B200_EXPAND", "slots")
+    for per_thread in ("1", "2", "5"):
+        monkeypatch.setenv("POCKIT_B200_SLOT_LISTS", per_thread)
+        bs = BatchedSystem(S, fixed)
+        try:
+            assert bs.engine.expand_kernel(P.JAC) == "pk_expand_slots" and bs.engine.expand_kernel(P.HESS) == "pk_expand_slots"
+            assert np.array_equal(bs.jacobian(X), jac) and np.array_equal(bs.hessian(X, LAM, sig), hess)
+        finally:
+            bs.close()
+    monkeypatch.delenv("POCKIT_B200_SLOT_LISTS")
     monkeypatch.delenv("POCKIT_B200_EXPAND")
     monkeypatch.setenv("POCKIT_B200_BATCH_TABLES", "1")
     bs = BatchedSystem(S, fixed)
