@@ -55,8 +55,8 @@ struct ExpandGroup {
   // bulk-store variant of it (opt-in): whole intervals per block, image handed to the TMA engine
   bool bulk = false; int xb_per_block = 0; unsigned xb_gx = 0; size_t xb_smem = 0;
   // batches of small problems: parameter-driven, (instance, pair) space flattened over the grid
-  bool batch = false; unsigned xbt_gx = 0; int batch_lists = PK_XM_LISTS, batch_rows = PK_XM_ROWS; size_t batch_smem = 0;
-  bool slots = false; unsigned xsl_gx = 0; int slot_lists = 2;  // pk_expand_slots (a batch variant)
+  bool batch = false; unsigned xbt_gx = 0; int batch_lists = PK_XM_LISTS, batch_rows = PK_XM_ROWS; size_t batch_smem = 0; unsigned n_groups = 0;
+  bool slots = false; unsigned xsl_gx = 0; int slot_lists = PK_XS_LISTS;  // pk_expand_slots (the default batch kernel)
 };
 
 struct ModeState {
@@ -422,13 +422,23 @@ static int build_block_map(const pk_job* jobs, long long n, int field, int per, 
   return 0;
 }
 
-// pk_expand_batch is instantiated for a few unrolled row counts; the smallest one that holds the block rows
-typedef void (*BatchKernel)(PkCtx, const PkXcParams, unsigned, int);
-static BatchKernel batch_kernel(bool lam, int rows) {
-#define PK_BK(R) if (rows <= R) return lam ? pk_expand_batch<true, R> : pk_expand_batch<false, R>;
-  PK_BK(4) PK_BK(5) PK_BK(6) PK_BK(8) PK_BK(10) PK_BK(12)
-#undef PK_BK
-  return lam ? pk_expand_batch<true, PK_XM_ROWS> : pk_expand_batch<false, PK_XM_ROWS>;
+// pk_expand_batch is instantiated for a few unrolled row counts (the smallest one that holds the block rows
+// is "exact"), with and without streaming stores
+typedef void (*BatchKernel)(PkCtx, const PkXcParams, unsigned);
+template <bool LAM, bool STREAM>
+static BatchKernel batch_kernel_of(int rows) {
+  if (rows <= 5) return pk_expand_batch<LAM, 5, STREAM>;
+  if (rows <= 8) return pk_expand_batch<LAM, 8, STREAM>;
+  if (rows <= 12) return pk_expand_batch<LAM, 12, STREAM>;
+  return pk_expand_batch<LAM, PK_XM_ROWS, STREAM>;
+}
+static BatchKernel batch_kernel(bool lam, int rows, bool stream) {
+  if (lam) return stream ? batch_kernel_of<true, true>(rows) : batch_kernel_of<true, false>(rows);
+  return stream ? batch_kernel_of<false, true>(rows) : batch_kernel_of<false, false>(rows);
+}
+static BatchKernel slots_kernel(bool lam, bool stream) {
+  if (lam) return stream ? pk_expand_slots<true, true> : pk_expand_slots<true, false>;
+  return stream ? pk_expand_slots<false, true> : pk_expand_slots<false, false>;
 }
 
 static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, long long count, ExpandGroup& g) {
@@ -476,9 +486,11 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
     g.batch = batch;
     g.xbt_gx = (unsigned)((max_pairs * e->dims.batch + PK_XC_THREADS - 1) / PK_XC_THREADS);
     if (batch) {
-      // slot-order variant (a thread per output slot, warps write consecutive doubles): POCKIT_B200_EXPAND=slots
+      // slot order (a thread per output slot, warps write consecutive doubles, all lists of a job per thread) is the
+      // default for batches: configs[4] set 264 -> 250 us (profiles/r02_call29_batch_loads_ahead.log);
+      // POCKIT_B200_EXPAND=batch selects the column mapping (pk_expand_batch), =slots insists on this one
       const char* env = getenv("POCKIT_B200_EXPAND");
-      g.slots = env && !strcmp(env, "slots");
+      g.slots = env ? !strcmp(env, "slots") : max_pairs * r0 * e->dims.batch < (1LL << 32);
       g.xsl_gx = (unsigned)((max_pairs * r0 * e->dims.batch + PK_XC_THREADS - 1) / PK_XC_THREADS);
       // experiment knobs: unrolled row count (exact = smallest instantiation that holds the rows; default 16) and
       // an unused dynamic shared-memory request that caps the resident blocks per SM
@@ -488,7 +500,9 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
         const long long v = atoll(psm);
         if (v > 0 && v <= 200 * 1024) {
           g.batch_smem = (size_t)v;
-          if (v > 48 * 1024) CK(cudaFuncSetAttribute((const void*)batch_kernel(g.lam, g.batch_rows), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v));
+          if (v > 48 * 1024)
+            for (int sw = 0; sw < 2; ++sw)
+              CK(cudaFuncSetAttribute((const void*)batch_kernel(g.lam, g.batch_rows, sw != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v));
         }
       }
       if (const char* pl = getenv("POCKIT_B200_BATCH_LISTS")) {
@@ -523,6 +537,16 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
       }
     }
     q.n_lists = li;
+    if (batch) {
+      // blockIdx.y of the batch kernels -> (job, first list, count)
+      const int per = g.slots ? g.slot_lists : g.batch_lists;
+      g.n_groups = 0;
+      for (int j = 0; j < q.n_jobs; ++j)
+        for (int l = 0; l < q.job[j].n_lists; l += per) {
+          const int cnt = q.job[j].n_lists - l < per ? q.job[j].n_lists - l : per;
+          q.grp[g.n_groups++] = (unsigned)j | ((unsigned)(q.job[j].list0 + l) << 8) | ((unsigned)cnt << 20);
+        }
+    }
     g.xc_gx = (unsigned)((max_pairs + PK_XC_THREADS - 1) / PK_XC_THREADS);
     auto kern = g.lam ? (const void*)pk_expand_cols<true> : (const void*)pk_expand_cols<false>;
     if (xsm > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
@@ -750,18 +774,11 @@ static void launch_expand(const ModeState& ms, const PkCtx& cx, int B, cudaStrea
       else
         pk_expand_bulk<false><<<grid, PK_XB_THREADS, g.xb_smem, st>>>(cx, g.xc, g.xb_per_block);
     } else if (g.batch && g.slots) {
-      unsigned groups = 0;
-      for (int j = 0; j < g.xc.n_jobs; ++j) groups += (unsigned)((g.xc.job[j].n_lists + g.slot_lists - 1) / g.slot_lists);
-      const dim3 grid(g.xsl_gx, groups);
-      if (g.lam)
-        pk_expand_slots<true><<<grid, PK_XC_THREADS, g.batch_smem <= 48 * 1024 ? g.batch_smem : 0, st>>>(cx, g.xc, (unsigned)B, g.slot_lists);
-      else
-        pk_expand_slots<false><<<grid, PK_XC_THREADS, g.batch_smem <= 48 * 1024 ? g.batch_smem : 0, st>>>(cx, g.xc, (unsigned)B, g.slot_lists);
+      const dim3 grid(g.xsl_gx, g.n_groups);
+      slots_kernel(g.lam, cx.stream != 0)<<<grid, PK_XC_THREADS, g.batch_smem <= 48 * 1024 ? g.batch_smem : 0, st>>>(cx, g.xc, (unsigned)B);
     } else if (g.batch) {
-      unsigned groups = 0;
-      for (int j = 0; j < g.xc.n_jobs; ++j) groups += (unsigned)((g.xc.job[j].n_lists + g.batch_lists - 1) / g.batch_lists);
-      const dim3 grid(g.xbt_gx, groups);
-      batch_kernel(g.lam, g.batch_rows)<<<grid, PK_XC_THREADS, g.batch_smem, st>>>(cx, g.xc, (unsigned)B, g.batch_lists);
+      const dim3 grid(g.xbt_gx, g.n_groups);
+      batch_kernel(g.lam, g.batch_rows, cx.stream != 0)<<<grid, PK_XC_THREADS, g.batch_smem, st>>>(cx, g.xc, (unsigned)B);
     } else if (g.cols) {
       const dim3 grid(g.xc_gx, (unsigned)g.xc.n_lists, B);
       if (g.lam)
@@ -1477,7 +1494,8 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
         std::vector<cudaGraphNode_t> nodes(n_nodes);
         if (n_nodes) CK(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
         const void* big[] = {(const void*)pk_expand_cols<true>, (const void*)pk_expand_cols<false>, (const void*)pk_expand_blocks,
-                             (const void*)pk_expand_slots<true>, (const void*)pk_expand_slots<false>};
+                             (const void*)slots_kernel(true, true), (const void*)slots_kernel(true, false),
+                             (const void*)slots_kernel(false, true), (const void*)slots_kernel(false, false)};
         for (cudaGraphNode_t nd : nodes) {
           cudaGraphNodeType ty;
           if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
@@ -1486,7 +1504,7 @@ static int run_set(pk_engine* e, const int* modes, int n_modes) {
           if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess) {
             for (const void* f : big) is_big = is_big || kp.func == f;
             for (int rr = 1; rr <= PK_XM_ROWS && !is_big; ++rr)
-              is_big = kp.func == (const void*)batch_kernel(true, rr) || kp.func == (const void*)batch_kernel(false, rr);
+              for (int v4 = 0; v4 < 4; ++v4) is_big = is_big || kp.func == (const void*)batch_kernel((v4 & 1) != 0, rr, (v4 & 2) != 0);
           } else {
             (void)cudaGetLastError();  // library (NVRTC) kernels: not a host function pointer -- small by construction
           }

@@ -343,6 +343,9 @@ struct PkXcParams {
   double sign;
   unsigned long long m_n;  // division multiplier of n
   unsigned long long m_bn; // division multiplier of n * rows
+  // batch kernels: blockIdx.y -> (job, first list, number of lists) of the group of lists a thread writes,
+  // packed as job | first << 8 | count << 20 (filled at set-up: no division or search in the kernel)
+  unsigned grp[PK_XC_LISTS];
   PkXcJob job[PK_XC_JOBS];
   PkXcList list[PK_XC_LISTS];
 };
@@ -410,6 +413,8 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
 // and found it slower there: that case is bound by the store streams, this one by instruction issue.)
 #define PK_XM_ROWS 16
 #define PK_XM_LISTS 2  // lists per thread
+#define PK_XM_AHEAD 4  // list values loaded ahead of the stores
+#define PK_XS_LISTS 8  // lists per thread of pk_expand_slots
 // ROWS >= rows is the unrolled trip count of the row loops.  The default launch uses ROWS = 16 for every
 // block shape: the exact instantiation (POCKIT_B200_BATCH_ROWS=exact) executes a third of the instructions
 // for 5-row blocks and needs 32 registers instead of 48, and is SLOWER on configs[4] (Jacobian expansion
@@ -417,22 +422,20 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_cols(PkCtx cx, const 
 // 34 KB apart, 16 resident blocks per SM push more of them at once than 10 do.  Capping the resident blocks
 // further (POCKIT_B200_BATCH_SMEM) is slower again (8 per SM: 276 us, 4: 326 us) -- profiles/
 // r02_call26_batch_rows_exact.log, r02_call27_batch_occupancy_cap.log.
-template <bool LAM, int ROWS>
-__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B,
-                                                                  int per_thread) {
+// STREAM: results written with streaming stores (cx.stream, decided at compile time here: a run-time test
+// costs two branches per store in these store-dominated loops)
+template <bool LAM, int ROWS, bool STREAM>
+__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B) {
   const int n = prm.n, rows = prm.rows;
   const int bn = n * rows;
-  // blockIdx.y enumerates (job, group of per_thread lists; PK_XM_LISTS unless overridden): a thread writes at most that many columns, so
-  // that jobs with many lists still spread over enough threads (8 lists per thread: 590 k threads for the
-  // quadrotor Jacobian, 80 us; 2 per thread as in its Hessian: 32 us for half the bytes)
-  int jj = 0, grp = (int)blockIdx.y;
-  while (grp >= (prm.job[jj].n_lists + per_thread - 1) / per_thread) {
-    grp -= (prm.job[jj].n_lists + per_thread - 1) / per_thread;
-    ++jj;
-  }
-  const PkXcJob& J = prm.job[jj];
-  const int l_lo = J.list0 + grp * per_thread;
-  const int l_hi = l_lo + per_thread < J.list0 + J.n_lists ? l_lo + per_thread : J.list0 + J.n_lists;
+  // blockIdx.y enumerates (job, group of lists; PK_XM_LISTS per group unless overridden): a thread writes at
+  // most that many columns, so that jobs with many lists still spread over enough threads (8 lists per
+  // thread: 590 k threads for the quadrotor Jacobian, 80 us; 2 per thread as in its Hessian: 32 us for half
+  // the bytes)
+  const unsigned gw = prm.grp[blockIdx.y];
+  const PkXcJob& J = prm.job[gw & 255u];
+  const int l_lo = (int)((gw >> 8) & 4095u);
+  const int l_hi = l_lo + (int)(gw >> 20);
   const unsigned t = blockIdx.x * PK_XC_THREADS + threadIdx.x;  // B * pairs < 2^32 (checked at set-up)
   if (t >= J.pairs * B) return;
   const unsigned b = pk_div(t, J.m_pairs);
@@ -453,42 +456,48 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const
   }
   const long long wofs = (long long)b * J.Lm + J.node0 + (long long)K * J.step + cc;
   double* __restrict__ out_b = cx.OUT + (long long)b * cx.n_out + (long long)K * bn + cc;
-  for (int li = l_lo; li < l_hi; ++li) {
-    const PkXcList& L = prm.list[li];
-    const double sv = cx.W[L.wbase + wofs];
-    double* __restrict__ out = out_b + L.dst;
+  // the list values of up to PK_XM_AHEAD lists are loaded before the first store: the compiler keeps a load
+  // behind the stores that precede it in program order (possible aliasing), which serialised one memory
+  // latency per list (ncu round 2: 21-32 long-scoreboard stall cycles per issue)
+  for (int l0 = l_lo; l0 < l_hi; l0 += PK_XM_AHEAD) {
+    double sv[PK_XM_AHEAD];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-      if (r < rows) pk_store(out + r * n, P[r] * sv, cx.stream);
+    for (int k = 0; k < PK_XM_AHEAD; ++k)
+      if (l0 + k < l_hi) sv[k] = cx.W[prm.list[l0 + k].wbase + wofs];
+#pragma unroll
+    for (int k = 0; k < PK_XM_AHEAD; ++k)
+      if (l0 + k < l_hi) {
+        double* __restrict__ out = out_b + prm.list[l0 + k].dst;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+          if (r < rows) pk_store(out + r * n, P[r] * sv[k], STREAM);
+      }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Slot-order variant of the batch expansion.  pk_expand_batch gives a thread a block COLUMN: with
-// 5 x 6 blocks a warp's store instruction then writes 48-byte pieces 240 bytes apart, every one of them a
-// partial 32-byte sector (ncu, round 2: 2.15 sector writes per sector of output, 41 MB of DRAM reads that
-// are fills of partially written sectors, 48 instructions per store instruction because the column set-up
-// is amortised over 10 stores only).  Here a thread owns one SLOT (instance, interval, row, column) of a
-// job -- the slots of one list of one instance are contiguous in the output, so a warp writes 32
-// consecutive doubles per list: whole sectors but for the two ends.  The factor
-// ((sign * unit[r][c]) * width) / 2 [* lambda_r] is formed once per thread and multiplies the list value
-// of each of the thread's lists: same association as every other expansion kernel, bit-identical
-// (tests/test_gpu_baseline_sizes.py).  Measured on B200 it is SLOWER than the column mapping (Jacobian
-// expansion 68 -> 77 us, set 263 -> 280-295 us, profiles/r02_call25_slot_order_batch.log): partial sectors
-// are not what bounds this case.  Opt-in only (POCKIT_B200_EXPAND=slots, POCKIT_B200_SLOT_LISTS).
-template <bool LAM>
-__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_slots(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B,
-                                                                  int per_thread) {
+// Slot-order batch expansion: the default for batches (configs[4]).  pk_expand_batch gives a thread a
+// block COLUMN: with 5 x 6 blocks a warp's store instruction then writes 48-byte pieces 240 bytes apart,
+// every one of them a partial 32-byte sector (ncu, round 2: 2.15 sector writes per sector of output).  Here
+// a thread owns one SLOT (instance, interval, row, column) of a job -- the slots of one list of one
+// instance are contiguous in the output, so a warp writes 32 consecutive doubles per list: whole sectors
+// but for the two ends.  The factor ((sign * unit[r][c]) * width) / 2 [* lambda_r] is formed once per thread
+// and multiplies the list value of each of the job's lists (PK_XS_LISTS per thread): same association as
+// every other expansion kernel, bit-identical (tests/test_gpu_baseline_sizes.py).
+// Measured on B200, configs[4] set: first version (one load, one store, next load ...) 280-295 us against
+// 263 us of the column mapping -- each list cost a full memory latency (ncu: 21 long-scoreboard stall
+// cycles per issue, 207 instructions per thread, a third of them the search for the list group).  With the
+// list values loaded ahead of the stores, the list groups from a parameter table and the streaming-store
+// switch a template argument: 250 us (column mapping with the same changes: 264 us) --
+// profiles/r02_call25_slot_order_batch.log, r02_ncu_batch_expansion_shapes.csv, r02_call29_batch_loads_ahead.log.
+template <bool LAM, bool STREAM>
+__global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_slots(PkCtx cx, const __grid_constant__ PkXcParams prm, unsigned B) {
   const unsigned n = (unsigned)prm.n, rows = (unsigned)prm.rows;
   const unsigned bn = n * rows;
-  int jj = 0, grp = (int)blockIdx.y;  // (job, group of per_thread lists)
-  while (grp >= (prm.job[jj].n_lists + per_thread - 1) / per_thread) {
-    grp -= (prm.job[jj].n_lists + per_thread - 1) / per_thread;
-    ++jj;
-  }
-  const PkXcJob& J = prm.job[jj];
-  const int l_lo = J.list0 + grp * per_thread;
-  const int l_hi = l_lo + per_thread < J.list0 + J.n_lists ? l_lo + per_thread : J.list0 + J.n_lists;
+  const unsigned gw = prm.grp[blockIdx.y];  // (job, group of lists)
+  const PkXcJob& J = prm.job[gw & 255u];
+  const int l_lo = (int)((gw >> 8) & 4095u);
+  const int l_hi = l_lo + (int)(gw >> 20);
   const unsigned run = J.pairs * rows;
   const unsigned t = blockIdx.x * PK_XC_THREADS + threadIdx.x;  // B * run < 2^32 (checked at set-up)
   if (t >= run * B) return;
@@ -502,9 +511,14 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_slots(PkCtx cx, const
   double v = ((prm.sign * __ldg(cx.dpool + prm.unit + q)) * cx.dpool[J.width + K]) / 2.0;
   if (LAM) v = v * __ldg(cx.LAM + (long long)b * cx.m + J.lam0 + (long long)K * rows + r);
   double* __restrict__ out_b = cx.OUT + (long long)b * cx.n_out + s;
-  for (int li = l_lo; li < l_hi; ++li) {
-    const PkXcList& L = prm.list[li];
-    pk_store(out_b + L.dst, v * wp[L.wbase], cx.stream);
+  for (int l0 = l_lo; l0 < l_hi; l0 += PK_XM_AHEAD) {  // loads ahead of the stores, as in pk_expand_batch
+    double sv[PK_XM_AHEAD];
+#pragma unroll
+    for (int k = 0; k < PK_XM_AHEAD; ++k)
+      if (l0 + k < l_hi) sv[k] = wp[prm.list[l0 + k].wbase];
+#pragma unroll
+    for (int k = 0; k < PK_XM_AHEAD; ++k)
+      if (l0 + k < l_hi) pk_store(out_b + prm.list[l0 + k].dst, v * sv[k], STREAM);
   }
 }
 

@@ -7,8 +7,8 @@ those the oracle was pinned on).
     C4 rocket    LGL 2x5556x10   100 010 nodes   (two phases, FUNC-linked boundaries)
     C5 quadrotor LGL 14x6, B = 8192 instances differing in the FIXED initial state
 
-The block expansion (``phasebase.py:1120-1124, 1280-1285``) has four kernels (the fourth,
-pk_expand_batch, is exercised by the batched test); every test asserts
+The block expansion (``phasebase.py:1120-1124, 1280-1285``) has five kernels (the two for batches,
+pk_expand_slots and pk_expand_batch, are exercised by the batched test); every test asserts
 that the engine really launches the one it claims to test (``Engine.expand_kernel``):
 ``columns`` -> pk_expand_blocks (persistent), ``params`` -> pk_expand_cols (the default where a
 block is a whole number of 32-byte sectors: C2, the kernel the bench and the roofline figure run
@@ -130,9 +130,9 @@ def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath, monkeypatc
     sig = rng.uniform(0.5, 1.5, B)
     bs = BatchedSystem(S, fixed)
     try:
-        # 72 (interval, column) pairs per job and instance: the batch kernel (a thread owns one (instance,
-        # interval, column) of a job and writes that block column of every list of the job from registers)
-        assert bs.engine.expand_kernel(P.HESS) == "pk_expand_batch" and bs.engine.expand_kernel(P.JAC) == "pk_expand_batch"
+        # 84 (interval, column) pairs and 420 slots per list and instance: the slot-order batch kernel (a thread
+        # owns one (instance, interval, row, column) slot of a job and writes it for every list of the job)
+        assert bs.engine.expand_kernel(P.HESS) == "pk_expand_slots" and bs.engine.expand_kernel(P.JAC) == "pk_expand_slots"
         obj, grad, cons = bs.objective(X), bs.gradient(X), bs.constraints(X)
         jac, hess = bs.jacobian(X), bs.hessian(X, LAM, sig)
         r = bs.engine.evaluate(X, LAM, sig)
@@ -149,9 +149,9 @@ def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath, monkeypatc
         assert np.array_equal(bs.jacobian(X), jac) and np.array_equal(bs.hessian(X, LAM, sig), hess)
     finally:
         bs.close()
-    # the slot-order variant (a thread per output slot), with one and with several lists per thread
+    # the slot-order kernel with fewer lists per thread than the default (all of a job's)
     monkeypatch.setenv("POCKIT_B200_EXPAND", "slots")
-    for per_thread in ("1", "2", "5"):
+    for per_thread in ("1", "2"):
         monkeypatch.setenv("POCKIT_B200_SLOT_LISTS", per_thread)
         bs = BatchedSystem(S, fixed)
         try:
@@ -160,6 +160,20 @@ def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath, monkeypatc
         finally:
             bs.close()
     monkeypatch.delenv("POCKIT_B200_SLOT_LISTS")
+    # the column mapping (a thread per (instance, interval, column), block column in registers): 16 unrolled rows
+    # with two lists per thread, the exact row count with five
+    monkeypatch.setenv("POCKIT_B200_EXPAND", "batch")
+    for rows_mode, per_thread in (("", "2"), ("exact", "5")):
+        monkeypatch.setenv("POCKIT_B200_BATCH_ROWS", rows_mode)
+        monkeypatch.setenv("POCKIT_B200_BATCH_LISTS", per_thread)
+        bs = BatchedSystem(S, fixed)
+        try:
+            assert bs.engine.expand_kernel(P.JAC) == "pk_expand_batch" and bs.engine.expand_kernel(P.HESS) == "pk_expand_batch"
+            assert np.array_equal(bs.jacobian(X), jac) and np.array_equal(bs.hessian(X, LAM, sig), hess)
+        finally:
+            bs.close()
+    monkeypatch.delenv("POCKIT_B200_BATCH_ROWS")
+    monkeypatch.delenv("POCKIT_B200_BATCH_LISTS")
     monkeypatch.delenv("POCKIT_B200_EXPAND")
     monkeypatch.setenv("POCKIT_B200_BATCH_TABLES", "1")
     bs = BatchedSystem(S, fixed)

@@ -30,25 +30,30 @@ def check(S, name, env=None):
     eng.close()
     for k in (env or {}): os.environ.pop(k, None)
 import pockit_b200.radau as rad, pockit_b200.lobatto as lob
-check(problems.robot_arm(rad, mesh=64, num_point=20), "robot_arm 64x20 cols")
-check(problems.robot_arm(rad, mesh=64, num_point=20), "robot_arm 64x20 bulk", {"POCKIT_B200_EXPAND": "bulk"})
-check(problems.rocket(lob, mesh=120, num_point=10), "rocket 2x120x10 (bulk by default)")
-check(problems.rocket(lob, mesh=20, num_point=[4] * 6 + [7] * 8 + [3, 5, 5, 5, 8, 8]), "rocket hp mesh (persistent blocks)")
-check(problems.humanoid(lob, mesh=20, num_point=10), "humanoid 20x10")
-check(problems.general(lob), "general lgl")
-check(problems.general(rad), "general lgr")
+ONLY_BATCH = os.environ.get("PK_SAN_ONLY") == "batch"  # just the batch kernels (both thread mappings)
+if not ONLY_BATCH:
+  check(problems.robot_arm(rad, mesh=64, num_point=20), "robot_arm 64x20 cols")
+  check(problems.robot_arm(rad, mesh=64, num_point=20), "robot_arm 64x20 bulk", {"POCKIT_B200_EXPAND": "bulk"})
+  check(problems.rocket(lob, mesh=120, num_point=10), "rocket 2x120x10 (bulk by default)")
+  check(problems.rocket(lob, mesh=20, num_point=[4] * 6 + [7] * 8 + [3, 5, 5, 5, 8, 8]), "rocket hp mesh (persistent blocks)")
+  check(problems.humanoid(lob, mesh=20, num_point=10), "humanoid 20x10")
+  check(problems.general(lob), "general lgl")
+  check(problems.general(rad), "general lgr")
 S = problems.quadrotor(lob, fastmath=False)
 B = 64
-bs = BatchedSystem(S, fixed_table(S, B))
 x0, lam0, _ = problems.evaluation_point(S)
 rng = np.random.default_rng(0)
 X = x0[None, :] + 1e-2 * rng.normal(size=(B, len(x0))); LAM = np.tile(lam0, (B, 1)); sig = np.ones(B)
-J = bs.jacobian(X); H = bs.hessian(X, LAM, sig); C = bs.constraints(X); G = bs.gradient(X)
 O = OracleSystem(S)
-ok = all(np.allclose(J[b], O.jacobian(X[b]), rtol=1e-12, atol=1e-14) and np.allclose(H[b], O.hessian(X[b], LAM[b], 1.0), rtol=1e-12, atol=1e-14) for b in (0, 17, 63))
-print("quadrotor batch 64", bs.engine.expand_kernel(P.JAC), "ok" if ok else "MISMATCH", flush=True)
-bs.close()
-for g_ in range(3):
+for mapping in ("", "batch"):  # default (slot order) and the column mapping
+    if mapping: os.environ["POCKIT_B200_EXPAND"] = mapping
+    bs = BatchedSystem(S, fixed_table(S, B))
+    J = bs.jacobian(X); H = bs.hessian(X, LAM, sig); C = bs.constraints(X); G = bs.gradient(X)
+    ok = all(np.allclose(J[b], O.jacobian(X[b]), rtol=1e-12, atol=1e-14) and np.allclose(H[b], O.hessian(X[b], LAM[b], 1.0), rtol=1e-12, atol=1e-14) for b in (0, 17, 63))
+    print("quadrotor batch 64", bs.engine.expand_kernel(P.JAC), "ok" if ok else "MISMATCH", flush=True)
+    bs.close()
+    os.environ.pop("POCKIT_B200_EXPAND", None)
+for g_ in range(0 if ONLY_BATCH else 3):
     eng = Engine(problems.robot_arm(rad, mesh=150, num_point=12).lowering, shard=(g_, 3, [1.0, 2.0, 0.7]))
     eng.close()
 print("san target done", flush=True)
