@@ -228,8 +228,8 @@ int pk_timeline(pk_engine *e, const int *modes, int n_modes, double *rows, int m
  * mix of orders [kernel pk_expand_blocks], 2 the parameter-driven column walk for same-order
  * meshes [kernel pk_expand_cols], 3 its opt-in TMA bulk-store variant [kernel pk_expand_bulk],
  * 4 the parameter-driven walk over the flattened (instance, pair) space of a batch [kernel pk_expand_batch;
- * POCKIT_B200_EXPAND=batch], 5 the slot-order batch kernel, a thread per output slot: the default for batches
- * [kernel pk_expand_slots] */
+ * POCKIT_B200_EXPAND=batch], 5 the slot-order batch kernel, a thread per output slot: the default for batch groups
+ * of jobs with three or more lists each, 4 for the others [kernel pk_expand_slots] */
 int pk_expand_variant(pk_engine *e, int mode, int *variant);
 int pk_kernel_launches(pk_engine *e, int64_t *count);
 /* process-wide cache of NVRTC results keyed by (architecture, options, source): the generated

@@ -489,8 +489,13 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
       // slot order (a thread per output slot, warps write consecutive doubles, all lists of a job per thread) is the
       // default for batches: configs[4] set 264 -> 250 us (profiles/r02_call29_batch_loads_ahead.log);
       // POCKIT_B200_EXPAND=batch selects the column mapping (pk_expand_batch), =slots insists on this one
+      // Groups whose jobs have one or two lists each stay on the column mapping: the slot order amortises its
+      // per-slot index arithmetic over the lists of a job (quadrotor Hessian, 2 jobs of 1-2 lists: 37.3 us
+      // against 32.1; Jacobian, one job of 5 lists: 48.2 against 68.5 -- profiles/r02_final_stage_times_quadrotor.log)
       const char* env = getenv("POCKIT_B200_EXPAND");
-      g.slots = env ? !strcmp(env, "slots") : max_pairs * r0 * e->dims.batch < (1LL << 32);
+      long long most_lists = 0;
+      for (long long j = 0; j < count; ++j) most_lists = ej[j].i[1] > most_lists ? ej[j].i[1] : most_lists;
+      g.slots = env ? !strcmp(env, "slots") : (most_lists >= 3 && max_pairs * r0 * e->dims.batch < (1LL << 32));
       g.xsl_gx = (unsigned)((max_pairs * r0 * e->dims.batch + PK_XC_THREADS - 1) / PK_XC_THREADS);
       // experiment knobs: unrolled row count (exact = smallest instantiation that holds the rows; default 16) and
       // an unused dynamic shared-memory request that caps the resident blocks per SM

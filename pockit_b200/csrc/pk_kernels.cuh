@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(PK_XC_THREADS) pk_expand_batch(PkCtx cx, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// Slot-order batch expansion: the default for batches (configs[4]).  pk_expand_batch gives a thread a
+// Slot-order batch expansion: the default for batch groups whose jobs have three or more lists (configs[4] Jacobian).  pk_expand_batch gives a thread a
 // block COLUMN: with 5 x 6 blocks a warp's store instruction then writes 48-byte pieces 240 bytes apart,
 // every one of them a partial 32-byte sector (ncu, round 2: 2.15 sector writes per sector of output).  Here
 // a thread owns one SLOT (instance, interval, row, column) of a job -- the slots of one list of one

@@ -130,9 +130,10 @@ def test_quadrotor_8192_instances_match_per_instance_oracle(fastmath, monkeypatc
     sig = rng.uniform(0.5, 1.5, B)
     bs = BatchedSystem(S, fixed)
     try:
-        # 84 (interval, column) pairs and 420 slots per list and instance: the slot-order batch kernel (a thread
-        # owns one (instance, interval, row, column) slot of a job and writes it for every list of the job)
-        assert bs.engine.expand_kernel(P.HESS) == "pk_expand_slots" and bs.engine.expand_kernel(P.JAC) == "pk_expand_slots"
+        # 84 (interval, column) pairs and 420 slots per list and instance.  Jacobian (one job of five lists): the
+        # slot-order batch kernel (a thread owns one (instance, interval, row, column) slot of a job and writes it
+        # for every list of the job); Hessian (jobs of one or two lists): the column mapping
+        assert bs.engine.expand_kernel(P.JAC) == "pk_expand_slots" and bs.engine.expand_kernel(P.HESS) == "pk_expand_batch"
         obj, grad, cons = bs.objective(X), bs.gradient(X), bs.constraints(X)
         jac, hess = bs.jacobian(X), bs.hessian(X, LAM, sig)
         r = bs.engine.evaluate(X, LAM, sig)
