@@ -486,12 +486,13 @@ static int setup_expand_group(pk_engine* e, const pk_job* ej, long long first, l
     g.batch = batch;
     g.xbt_gx = (unsigned)((max_pairs * e->dims.batch + PK_XC_THREADS - 1) / PK_XC_THREADS);
     if (batch) {
-      // slot order (a thread per output slot, warps write consecutive doubles, all lists of a job per thread) is the
-      // default for batches: configs[4] set 264 -> 250 us (profiles/r02_call29_batch_loads_ahead.log);
-      // POCKIT_B200_EXPAND=batch selects the column mapping (pk_expand_batch), =slots insists on this one
-      // Groups whose jobs have one or two lists each stay on the column mapping: the slot order amortises its
-      // per-slot index arithmetic over the lists of a job (quadrotor Hessian, 2 jobs of 1-2 lists: 37.3 us
-      // against 32.1; Jacobian, one job of 5 lists: 48.2 against 68.5 -- profiles/r02_final_stage_times_quadrotor.log)
+      // Two thread mappings.  Slot order (pk_expand_slots: a thread per output slot, warps write consecutive
+      // doubles, all lists of a job per thread) for groups whose jobs have three or more lists: it amortises its
+      // per-slot index arithmetic over the lists of a job (quadrotor Jacobian, one job of 5 lists: 48.2 us against
+      // 68.5).  The column mapping (pk_expand_batch) for the others (quadrotor Hessian, 2 jobs of 1-2 lists: 32.1 us
+      // against 37.3).  configs[4] set 264 -> 243 us (profiles/r02_call29_batch_loads_ahead.log,
+      // r02_final_stage_times_quadrotor.log, r02_call30_batch_mapping_per_group.log).
+      // POCKIT_B200_EXPAND=batch | slots forces one of them for every group.
       const char* env = getenv("POCKIT_B200_EXPAND");
       long long most_lists = 0;
       for (long long j = 0; j < count; ++j) most_lists = ej[j].i[1] > most_lists ? ej[j].i[1] : most_lists;
